@@ -1,0 +1,204 @@
+"""ctypes binding of libmpcb200.so (include/mpcb200.h).
+
+This is the only way the package computes an MPC solve: there is NO CPU fallback.
+If the shared library is missing it is built with nvcc (diplomjourney_b200.build);
+if that is impossible, or no CUDA device is present, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MODE_FULL, MODE_HELD = 0, 1
+COST_MM, COST_TREE = 0, 1
+ALGO_AUTO, ALGO_LEAFWALK, ALGO_PREFIX = 0, 1, 2
+FLAG_SLOW = 1
+MAX_H = 8
+
+_ERR = {-1: "invalid argument", -2: "CUDA error", -3: "no grid set", -4: "empty control grid",
+        -5: "tree too large", -6: "no CUDA device", -7: "NCCL error"}
+
+
+class MpcbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmpcb200: {_ERR.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("units", C.c_int64), ("leaves_per_solve", C.c_int64), ("segments", C.c_int64),
+                ("refine_segments", C.c_int64), ("refine_candidates", C.c_int64),
+                ("algo", C.c_int32), ("kernel_launches", C.c_int32)]
+
+
+_lib = None
+_dp, _i64p, _u8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) libmpcb200.so. Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build_library()
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.mpcb_version.restype = C.c_int
+    lib.mpcb_device_count.restype = C.c_int
+    lib.mpcb_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.mpcb_destroy.argtypes = [vp]
+    lib.mpcb_last_error.argtypes = [vp]
+    lib.mpcb_last_error.restype = C.c_char_p
+    lib.mpcb_stream.argtypes = [vp]
+    lib.mpcb_stream.restype = vp
+    lib.mpcb_sync.argtypes = [vp]
+    lib.mpcb_set_grid.argtypes = [vp, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double]
+    lib.mpcb_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    solve = [vp, C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp]
+    lib.mpcb_solve_batch_host.argtypes = solve
+    lib.mpcb_solve_batch_device.argtypes = solve
+    lib.mpcb_dump_leaves_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_uint8,
+                                          C.c_int64, C.c_int64, _fp, _dp]
+    lib.mpcb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.mpcb_allreduce_min.argtypes = [vp, vp, vp, vp]
+    lib.mpcb_nccl_unique_id.argtypes = [vp]
+    lib.mpcb_nccl_comm_create.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    lib.mpcb_nccl_comm_destroy.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _arr(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Solver:
+    """One device, one stream, one control grid at a time (mpcb_handle)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.mpcb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise MpcbError(rc, "mpcb_create failed (a CUDA device is required; there is no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+        self.S = 0
+        self.grid = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpcb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MpcbError(rc, (self.lib.mpcb_last_error(self.h) or b"").decode())
+
+    # ---- configuration
+    def set_grid(self, vector_v, vector_beta, L, delta_t, v_min=0.0):
+        v = _arr(vector_v, np.float64).ravel()
+        b = _arr(vector_beta, np.float64).ravel()
+        self._ck(self.lib.mpcb_set_grid(self.h, v.ctypes.data_as(_dp), v.size, b.ctypes.data_as(_dp), b.size,
+                                        float(L), float(delta_t), float(v_min)))
+        self.S = v.size * b.size
+        self.grid = (v, b, float(L), float(delta_t), float(v_min))
+
+    def set_option(self, name: str, value: float):
+        self._ck(self.lib.mpcb_set_option(self.h, name.encode(), float(value)))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.mpcb_stream(self.h) or 0)
+
+    def sync(self):
+        self._ck(self.lib.mpcb_sync(self.h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self.lib.mpcb_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    # ---- solves
+    def solve(self, mode, cost, H, state, target, origin, threshold=None, flags=None, i0_range=None):
+        """Host-buffer batch solve (mpcb_solve_batch_host). Arrays: state[N,3], target[N,2], origin[N,2]."""
+        st = _arr(state, np.float64)
+        st = st.reshape(-1, st.shape[-1])[:, :3].copy() if st.ndim > 1 else st[:3].reshape(1, 3).copy()
+        N = st.shape[0]
+        tg = _arr(target, np.float64, (-1, 2))
+        og = _arr(origin, np.float64, (-1, 2))
+        if tg.shape[0] == 1 and N > 1:
+            tg = np.repeat(tg, N, 0)
+        if og.shape[0] == 1 and N > 1:
+            og = np.repeat(og, N, 0)
+        if tg.shape[0] != N or og.shape[0] != N:
+            raise ValueError("state/target/origin batch sizes differ")
+        thr = None if threshold is None else _arr(np.broadcast_to(np.asarray(threshold, np.float64), (N,)), np.float64)
+        fl = None if flags is None else _arr(np.broadcast_to(np.asarray(flags, np.uint8), (N,)), np.uint8)
+        lo, hi = (0, -1) if i0_range is None else (int(i0_range[0]), int(i0_range[1]))
+        cost_o = np.empty(N, np.float64)
+        idx_o = np.empty(N, np.int64)
+        traj_o = np.empty((N, H, 3), np.float64)
+        ctl_o = np.empty((N, 2), np.float64)
+        self._ck(self.lib.mpcb_solve_batch_host(self.h, mode, cost, H, N, _ptr(st), _ptr(tg), _ptr(og), _ptr(thr),
+                                                _ptr(fl), lo, hi, _ptr(cost_o), _ptr(idx_o), _ptr(traj_o), _ptr(ctl_o)))
+        return dict(cost=cost_o, index=idx_o, traj=traj_o, first_control=ctl_o)
+
+    def solve_device(self, mode, cost, H, N, state, target, origin, threshold, flags, out_cost, out_index,
+                     out_traj, out_ctl, i0_range=None):
+        """Device-pointer batch solve (mpcb_solve_batch_device); arguments are raw device addresses
+        (e.g. torch.Tensor.data_ptr()) or 0/None. Enqueues on self.stream, does not synchronise."""
+        lo, hi = (0, -1) if i0_range is None else (int(i0_range[0]), int(i0_range[1]))
+        vp = lambda x: C.c_void_p(int(x)) if x else None
+        self._ck(self.lib.mpcb_solve_batch_device(self.h, mode, cost, H, int(N), vp(state), vp(target), vp(origin),
+                                                  vp(threshold), vp(flags), lo, hi, vp(out_cost), vp(out_index),
+                                                  vp(out_traj), vp(out_ctl)))
+
+    def dump_leaves(self, mode, cost, H, state, target, origin, flags=0, algo=ALGO_LEAFWALK, leaf_begin=0, count=None):
+        st = _arr(state, np.float64).ravel()[:3].copy()
+        tg = _arr(target, np.float64).ravel()[:2].copy()
+        og = _arr(origin, np.float64).ravel()[:2].copy()
+        if count is None:
+            count = (self.S if mode == MODE_HELD else self.S ** H) - leaf_begin
+        xy = np.empty((count, 2), np.float32)
+        cs = np.empty(count, np.float64)
+        self._ck(self.lib.mpcb_dump_leaves_host(self.h, mode, cost, H, algo, st.ctypes.data_as(_dp),
+                                                tg.ctypes.data_as(_dp), og.ctypes.data_as(_dp), int(flags),
+                                                int(leaf_begin), int(count), xy.ctypes.data_as(_fp),
+                                                cs.ctypes.data_as(_dp)))
+        return xy, cs
+
+
+_default = {}
+
+
+def default_solver(device: int = 0) -> Solver:
+    """Process-wide solver per device used by the reference-API modules."""
+    s = _default.get(device)
+    if s is None:
+        s = _default[device] = Solver(device)
+    return s

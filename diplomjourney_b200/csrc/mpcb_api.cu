@@ -1,0 +1,476 @@
+// mpcb_api.cu -- host side of the C ABI declared in include/mpcb200.h.
+//
+// One handle = one device + one stream + growable device scratch.  A solve enqueues
+//   prep -> pass 1 (partial minima) -> reduce+compact -> pass 2 (float64 refinement) -> finalize
+// on the handle's stream; the "_host" entry points add the H2D/D2H copies and a sync.
+#include "../../include/mpcb200.h"
+#include "mpcb_types.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace mpcb {
+cudaError_t launch_prep(cudaStream_t, long long, const double *, const double *, const double *, const double *,
+                        const uint8_t *, int, int, int, double, double, double, SolveParams *);
+cudaError_t launch_pass(cudaStream_t, const LaunchArgs &, int pass, bool prefix, int sms);
+cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, unsigned *, unsigned *, int sms);
+cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
+cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
+}  // namespace mpcb
+
+using namespace mpcb;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+constexpr unsigned long long kSegCap = 1ULL << 22;
+
+void fastdiv_init(FastDiv64 &f, unsigned long long d) {
+    f.d = d;
+    if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
+    unsigned l = 0;
+    while ((l < 64) && ((1ULL << l) < d)) ++l;            // ceil(log2 d), d < 2^63
+    unsigned __int128 num = ((unsigned __int128)1 << 64) * (((unsigned __int128)1 << l) - d);
+    f.m = (unsigned long long)(num / d) + 1ULL;
+    f.sh1 = 1; f.sh2 = l - 1;
+}
+
+}  // namespace
+
+struct mpcb_handle_s {
+    int device = 0, sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // grid
+    bool have_grid = false;
+    GridTables g{};
+    DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, ctl32, ctl32_slow;
+    // options
+    double tol_scale = 1.0;
+    int algo = MPCB_ALGO_AUTO;
+    int refine = 1;
+    // scratch
+    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock;
+    DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
+    mpcb_stats stats{};
+    unsigned long long last_counters_pending = 0;
+};
+
+namespace {
+
+int fail(mpcb_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(h, MPCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// S^H as unsigned 64-bit with overflow check against int64
+bool pow_checked(unsigned long long S, int H, unsigned long long &out) {
+    unsigned __int128 r = 1;
+    for (int i = 0; i < H; ++i) {
+        r *= S;
+        if (r > (unsigned __int128)INT64_MAX) return false;
+    }
+    out = (unsigned long long)r;
+    return true;
+}
+
+struct Plan {
+    bool prefix;
+    unsigned long long u_begin, u_end, leaves_per_solve;
+};
+
+int make_plan(mpcb_handle *h, int mode, int H, long long N, long long i0_begin, long long i0_end, int algo_req,
+              Plan &pl) {
+    const unsigned long long S = (unsigned long long)h->g.S;
+    if (mode == MPCB_MODE_HELD) {
+        pl.prefix = false;
+        pl.u_begin = 0; pl.u_end = S; pl.leaves_per_solve = S;
+        return MPCB_OK;
+    }
+    unsigned long long leaves, sub;
+    if (!pow_checked(S, H, leaves)) return fail(h, MPCB_ERR_TOO_LARGE, "S^H = %llu^%d exceeds int64", S, H);
+    pow_checked(S, H - 1, sub);
+    if (i0_end < 0) { i0_begin = 0; i0_end = (long long)S; }
+    if (i0_begin < 0 || i0_end > (long long)S || i0_begin > i0_end)
+        return fail(h, MPCB_ERR_INVALID, "bad first-control range [%lld,%lld) for S=%llu", i0_begin, i0_end, S);
+    int algo = algo_req == MPCB_ALGO_AUTO ? h->algo : algo_req;
+    unsigned long long parents = H >= 2 ? sub / 1 : 0;   // S^(H-1)
+    if (algo == MPCB_ALGO_AUTO)
+        algo = (H >= 2 && (unsigned __int128)parents * (unsigned long long)N >= 32768) ? MPCB_ALGO_PREFIX
+                                                                                       : MPCB_ALGO_LEAFWALK;
+    if (H < 2) algo = MPCB_ALGO_LEAFWALK;
+    pl.prefix = algo == MPCB_ALGO_PREFIX;
+    if (pl.prefix) {
+        unsigned long long per_i0 = sub / S;   // S^(H-2) depth-(H-1) nodes below one first control
+        pl.u_begin = (unsigned long long)i0_begin * per_i0;
+        pl.u_end = (unsigned long long)i0_end * per_i0;
+    } else {
+        pl.u_begin = (unsigned long long)i0_begin * sub;
+        pl.u_end = (unsigned long long)i0_end * sub;
+    }
+    pl.leaves_per_solve = (unsigned long long)(i0_end - i0_begin) * sub;
+    return MPCB_OK;
+}
+
+void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, long long N, const Plan &pl) {
+    memset(&a, 0, sizeof a);
+    a.g = h->g;
+    a.mode = mode; a.H = H; a.cost_kind = cost_kind; a.refine = h->refine;
+    a.N = N;
+    unsigned long long S = (unsigned long long)h->g.S, pw = 1;
+    for (int k = H - 1; k >= 0; --k) {   // fd[k].d = S^(H-1-k)
+        fastdiv_init(a.fd[k], pw);
+        if (mode == MPCB_MODE_FULL) pw *= S;
+    }
+    a.u_begin = pl.u_begin; a.u_end = pl.u_end;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpcb_version(void) { return 100; }
+
+int mpcb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int mpcb_create(int device_ordinal, mpcb_handle **out) {
+    if (!out) return MPCB_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return MPCB_ERR_NO_DEVICE;
+    if (device_ordinal < 0 || device_ordinal >= n) return MPCB_ERR_INVALID;
+    mpcb_handle *h = new mpcb_handle_s();
+    h->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return MPCB_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device_ordinal);
+    *out = h;
+    return MPCB_OK;
+}
+
+int mpcb_destroy(mpcb_handle *h) {
+    if (!h) return MPCB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->ctl32,
+                      &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
+                      &h->lock, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
+                      &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j})
+        b->release();
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MPCB_OK;
+}
+
+const char *mpcb_last_error(const mpcb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+void *mpcb_stream(mpcb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int mpcb_sync(mpcb_handle *h) {
+    if (!h) return MPCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCB_OK;
+}
+
+int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
+    if (!h || !name) return MPCB_ERR_INVALID;
+    if (!strcmp(name, "tol_scale")) h->tol_scale = value;
+    else if (!strcmp(name, "algo")) h->algo = (int)value;
+    else if (!strcmp(name, "refine")) h->refine = value != 0.0;
+    else return fail(h, MPCB_ERR_INVALID, "unknown option '%s'", name);
+    return MPCB_OK;
+}
+
+int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, int nb, double L, double delta_t,
+                  double v_min) {
+    if (!h || (!v && nv) || (!beta && nb) || nv < 0 || nb < 0) return fail(h, MPCB_ERR_INVALID, "set_grid: bad arguments");
+    if (nv == 0 || nb == 0) { h->have_grid = false; return fail(h, MPCB_ERR_EMPTY_GRID, "empty control grid"); }
+    if ((long long)nv * nb > (1LL << 30)) return fail(h, MPCB_ERR_TOO_LARGE, "grid too large");
+    CK(cudaSetDevice(h->device));
+    const int S = nv * nb;
+    std::vector<double4> t64(S), t64s(S);
+    std::vector<double> vt(S), vts(S);
+    std::vector<float4> l32(S);
+    std::vector<float2> c32(S), c32s(S);
+    double vmin_grid = v[0];
+    for (int i = 1; i < nv; ++i) vmin_grid = std::min(vmin_grid, v[i]);
+    const double v_slow = vmin_grid > v_min ? vmin_grid : v_min;   // math_model_tree.py:312-316
+    double smax = 0, dphimax = 0;
+    for (int iv = 0; iv < nv; ++iv)
+        for (int ib = 0; ib < nb; ++ib) {
+            const int c = iv * nb + ib;
+            for (int variant = 0; variant < 2; ++variant) {
+                const double vc = variant ? v_slow : v[iv];
+                const double dphi = (vc / L) * std::tan(beta[ib]) * delta_t;   // math_model.py:77-78 x delta_t
+                const double s = vc * delta_t;
+                const double cd = std::cos(dphi), sd = std::sin(dphi);
+                smax = std::max(smax, std::fabs(s));
+                dphimax = std::max(dphimax, std::fabs(dphi));
+                if (variant == 0) {
+                    t64[c] = make_double4(cd, sd, s, dphi);
+                    vt[c] = vc;
+                    l32[c] = make_float4((float)(s * cd), (float)(s * sd), (float)(s * s),
+                                         (float)(3.16227766016837952 * dphi));
+                    c32[c] = make_float2((float)dphi, (float)s);
+                } else {
+                    t64s[c] = make_double4(cd, sd, s, dphi);
+                    vts[c] = vc;
+                    c32s[c] = make_float2((float)dphi, (float)s);
+                }
+            }
+        }
+    CK(h->tab64.ensure(sizeof(double4) * S)); CK(h->tab64_slow.ensure(sizeof(double4) * S));
+    CK(h->vtab.ensure(sizeof(double) * S)); CK(h->vtab_slow.ensure(sizeof(double) * S));
+    CK(h->beta.ensure(sizeof(double) * nb));
+    CK(h->leaf32.ensure(sizeof(float4) * S));
+    CK(h->ctl32.ensure(sizeof(float2) * S)); CK(h->ctl32_slow.ensure(sizeof(float2) * S));
+    // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may die here;
+    // ordering against earlier solves on the stream is preserved
+    CK(cudaMemcpyAsync(h->tab64.p, t64.data(), sizeof(double4) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tab64_slow.p, t64s.data(), sizeof(double4) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->vtab.p, vt.data(), sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->vtab_slow.p, vts.data(), sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->beta.p, beta, sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->leaf32.p, l32.data(), sizeof(float4) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ctl32.p, c32.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ctl32_slow.p, c32s.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    GridTables &g = h->g;
+    g.tab64 = h->tab64.as<double4>(); g.vtab = h->vtab.as<double>();
+    g.tab64_slow = h->tab64_slow.as<double4>(); g.vtab_slow = h->vtab_slow.as<double>();
+    g.beta = h->beta.as<double>();
+    g.leaf32 = h->leaf32.as<float4>();
+    g.ctl32 = h->ctl32.as<float2>(); g.ctl32_slow = h->ctl32_slow.as<float2>();
+    g.S = S; g.nb = nb; g.dt = delta_t; g.smax = smax; g.dphimax = dphimax;
+    h->have_grid = true;
+    return MPCB_OK;
+}
+
+int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                            const double *target, const double *origin, const double *threshold,
+                            const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
+                            int64_t *best_index, double *best_traj, double *first_control) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
+    if (H < 1 || H > MPCB_MAX_H) return fail(h, MPCB_ERR_INVALID, "H=%d out of range [1,%d]", H, MPCB_MAX_H);
+    if ((mode != MPCB_MODE_FULL && mode != MPCB_MODE_HELD) || (cost_kind != MPCB_COST_MM && cost_kind != MPCB_COST_TREE))
+        return fail(h, MPCB_ERR_INVALID, "bad mode/cost");
+    if (N < 0 || N >= (1LL << 31)) return fail(h, MPCB_ERR_INVALID, "N out of range");
+    if (N == 0) return MPCB_OK;
+    if (!state || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
+    CK(cudaSetDevice(h->device));
+    Plan pl;
+    int rc = make_plan(h, mode, H, N, i0_begin, i0_end, MPCB_ALGO_AUTO, pl);
+    if (rc) return rc;
+
+    LaunchArgs a;
+    fill_args(h, a, mode, cost_kind, H, N, pl);
+    const unsigned long long units = pl.u_end - pl.u_begin;
+    a.tiles_per_solve = (units + kThreads - 1) / kThreads;
+    unsigned __int128 all_tiles = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
+    unsigned long long tps = (unsigned long long)((all_tiles + kSegCap - 1) / kSegCap);
+    if (tps < 1) tps = 1;
+    if (tps >= (1ULL << 32)) return fail(h, MPCB_ERR_TOO_LARGE, "tree too large for one launch; split by first control");
+    a.tps = (unsigned)tps;
+    a.segs_per_solve = a.tiles_per_solve ? (a.tiles_per_solve + tps - 1) / tps : 0;
+    a.total_segs = a.segs_per_solve * (unsigned long long)N;
+    if (a.total_segs >= (1ULL << 32)) return fail(h, MPCB_ERR_TOO_LARGE, "too many segments");
+
+    CK(h->sp.ensure(sizeof(SolveParams) * N));
+    CK(h->segmin.ensure(sizeof(double) * std::max<unsigned long long>(a.total_segs, 1)));
+    CK(h->worklist.ensure(sizeof(unsigned) * std::max<unsigned long long>(a.total_segs, 1)));
+    CK(h->misc.ensure(64));
+    CK(h->tau.ensure(sizeof(double) * N));
+    CK(h->bestJ.ensure(sizeof(double) * N));
+    CK(h->bestIdx.ensure(sizeof(long long) * N));
+    CK(h->lock.ensure(sizeof(int) * N));
+    // misc: [0..7] work_count (u32) | [16..31] counters (2 x u64)
+    unsigned *work_count = h->misc.as<unsigned>();
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
+    CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
+
+    a.sp = h->sp.as<SolveParams>();
+    a.segmin = h->segmin.as<double>();
+    a.worklist = h->worklist.as<unsigned>();
+    a.work_count = work_count;
+    a.bestJ = h->bestJ.as<double>();
+    a.bestIdx = h->bestIdx.as<long long>();
+    a.lock = h->lock.as<int>();
+    a.counters = counters;
+    a.tau = h->tau.as<double>();
+
+    int launches = 0;
+    CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, pl.prefix ? 1 : 0,
+                   h->g.smax, h->g.dphimax, h->tol_scale, h->sp.as<SolveParams>())); ++launches;
+    if (a.total_segs > 0) {
+        CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
+    }
+    CK(launch_reduce_compact(h->stream, a, h->tau.as<double>(), h->worklist.as<unsigned>(), work_count, h->sms)); ++launches;
+    if (a.total_segs > 0) {
+        CK(launch_pass(h->stream, a, 2, pl.prefix, h->sms)); ++launches;
+    }
+    CK(launch_finalize(h->stream, a, best_cost, (long long *)best_index, best_traj, first_control)); ++launches;
+
+    h->stats.units = (int64_t)units;
+    h->stats.leaves_per_solve = (int64_t)pl.leaves_per_solve;
+    h->stats.segments = (int64_t)a.total_segs;
+    h->stats.algo = pl.prefix ? MPCB_ALGO_PREFIX : MPCB_ALGO_LEAFWALK;
+    h->stats.kernel_launches = launches;
+    h->stats.refine_segments = -1;   // resolved lazily by mpcb_get_stats
+    h->stats.refine_candidates = -1;
+    return MPCB_OK;
+}
+
+int mpcb_get_stats(mpcb_handle *h, mpcb_stats *out) {
+    if (!h || !out) return MPCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (h->stats.refine_segments < 0 && h->misc.p) {
+        unsigned long long c[2] = {0, 0};
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(c, h->misc.as<char>() + 16, sizeof c, cudaMemcpyDeviceToHost));
+        h->stats.refine_segments = (int64_t)c[0];
+        h->stats.refine_candidates = (int64_t)c[1];
+    }
+    *out = h->stats;
+    return MPCB_OK;
+}
+
+int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                          const double *target, const double *origin, const double *threshold,
+                          const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
+                          int64_t *best_index, double *best_traj, double *first_control) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
+    if (!state || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
+    if (H < 1 || H > MPCB_MAX_H) return fail(h, MPCB_ERR_INVALID, "H=%d out of range [1,%d]", H, MPCB_MAX_H);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CK(h->in_state.ensure(sizeof(double) * 3 * N));
+    CK(h->in_target.ensure(sizeof(double) * 2 * N));
+    CK(h->in_origin.ensure(sizeof(double) * 2 * N));
+    CK(cudaMemcpyAsync(h->in_state.p, state, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_target.p, target, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_origin.p, origin, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    const double *d_thr = nullptr;
+    const uint8_t *d_flags = nullptr;
+    if (threshold) {
+        CK(h->in_thr.ensure(sizeof(double) * N));
+        CK(cudaMemcpyAsync(h->in_thr.p, threshold, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        d_thr = h->in_thr.as<double>();
+    }
+    if (flags) {
+        CK(h->in_flags.ensure(N));
+        CK(cudaMemcpyAsync(h->in_flags.p, flags, N, cudaMemcpyHostToDevice, st));
+        d_flags = h->in_flags.as<uint8_t>();
+    }
+    CK(h->out_cost.ensure(sizeof(double) * N));
+    CK(h->out_index.ensure(sizeof(int64_t) * N));
+    CK(h->out_traj.ensure(sizeof(double) * 3 * H * N));
+    CK(h->out_ctl.ensure(sizeof(double) * 2 * N));
+    int rc = mpcb_solve_batch_device(h, mode, cost_kind, H, N, h->in_state.as<double>(), h->in_target.as<double>(),
+                                     h->in_origin.as<double>(), d_thr, d_flags, i0_begin, i0_end,
+                                     h->out_cost.as<double>(), h->out_index.as<int64_t>(), h->out_traj.as<double>(),
+                                     h->out_ctl.as<double>());
+    if (rc) return rc;
+    if (best_cost) CK(cudaMemcpyAsync(best_cost, h->out_cost.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (best_index) CK(cudaMemcpyAsync(best_index, h->out_index.p, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, st));
+    if (best_traj) CK(cudaMemcpyAsync(best_traj, h->out_traj.p, sizeof(double) * 3 * H * N, cudaMemcpyDeviceToHost, st));
+    if (first_control) CK(cudaMemcpyAsync(first_control, h->out_ctl.p, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MPCB_OK;
+}
+
+int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int algo, const double *state,
+                          const double *target, const double *origin, uint8_t flags, int64_t leaf_begin,
+                          int64_t count, float *xy, double *cost) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
+    if (H < 1 || H > MPCB_MAX_H || count < 0 || leaf_begin < 0 || !state || !target || !origin)
+        return fail(h, MPCB_ERR_INVALID, "dump: bad arguments");
+    if (count == 0) return MPCB_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    Plan pl;
+    int rc = make_plan(h, mode, H, 1, 0, -1, algo == MPCB_ALGO_AUTO ? MPCB_ALGO_LEAFWALK : algo, pl);
+    if (rc) return rc;
+    if ((unsigned long long)(leaf_begin + count) > pl.leaves_per_solve)
+        return fail(h, MPCB_ERR_INVALID, "dump range exceeds the %llu leaves of the tree", pl.leaves_per_solve);
+    LaunchArgs a;
+    fill_args(h, a, mode, cost_kind, H, 1, pl);
+    CK(h->in_state.ensure(sizeof(double) * 3)); CK(h->in_target.ensure(sizeof(double) * 2));
+    CK(h->in_origin.ensure(sizeof(double) * 2)); CK(h->in_flags.ensure(1));
+    CK(cudaMemcpyAsync(h->in_state.p, state, sizeof(double) * 3, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_target.p, target, sizeof(double) * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_origin.p, origin, sizeof(double) * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_flags.p, &flags, 1, cudaMemcpyHostToDevice, st));
+    CK(h->sp.ensure(sizeof(SolveParams)));
+    CK(h->dump_rec.ensure(sizeof(float4) * count));
+    CK(h->dump_j.ensure(sizeof(double) * count));
+    CK(launch_prep(st, 1, h->in_state.as<double>(), h->in_target.as<double>(), h->in_origin.as<double>(), nullptr,
+                   h->in_flags.as<uint8_t>(), cost_kind, H, pl.prefix ? 1 : 0, h->g.smax, h->g.dphimax, h->tol_scale,
+                   h->sp.as<SolveParams>()));
+    a.sp = h->sp.as<SolveParams>();
+    a.dump = h->dump_rec.as<float4>();
+    a.dump_begin = (unsigned long long)leaf_begin;
+    a.dump_count = (unsigned long long)count;
+    // positions always come from the leafwalk kernel; costs from the requested algorithm
+    CK(launch_dump(st, a, false, h->dump_j.as<double>(), h->sms));
+    std::vector<float4> rec(count);
+    std::vector<double> jr(count);
+    CK(cudaMemcpyAsync(rec.data(), h->dump_rec.p, sizeof(float4) * count, cudaMemcpyDeviceToHost, st));
+    if (pl.prefix) {
+        // the prefix flavour needs the prefix-mode SolveParams (tolerance differs only), same anchors
+        CK(launch_dump(st, a, true, h->dump_j.as<double>(), h->sms));
+    }
+    CK(cudaMemcpyAsync(jr.data(), h->dump_j.p, sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+    SolveParams P;
+    CK(cudaMemcpyAsync(&P, h->sp.p, sizeof P, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < count; ++i) {
+        if (xy) { xy[2 * i] = rec[i].x; xy[2 * i + 1] = rec[i].y; }
+        if (cost) cost[i] = P.Kbase + jr[i];
+    }
+    return MPCB_OK;
+}
+
+}  // extern "C"

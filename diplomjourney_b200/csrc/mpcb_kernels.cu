@@ -1,0 +1,608 @@
+// mpcb_kernels.cu -- sm_100a kernels of the MPC inner loop.
+//
+// Reference semantics implemented here (paths into ShittyWizard/DiplomJourney):
+//   node step   iteration_of_predict          math_model.py:110-114
+//   cost        control_criterion             math_model.py:82-86 (MM), math_model_tree.py:82-87 (TREE)
+//   FULL tree   predictive_control            math_model.py:159-200
+//   HELD tree   predictive_control            math_model_tree.py:308-361, CoordinateTree.py:20-30
+//
+// Numerical scheme: every leaf cost is evaluated in fp32 as an OFFSET
+// from a float64 anchor, J = Kbase + base_p + L, where L is O(reach) instead of O(1e5); a
+// first pass keeps only partial minima, a second pass re-evaluates in float64 (reference
+// formula, reference operation order) the few leaves whose fp32 value lies inside a
+// rigorous error window above the minimum, so the selected leaf is the float64 argmin.
+//
+// Two expansion algorithms:
+//   leafwalk  one thread per leaf walks all H steps in registers (sin.approx/cos.approx)
+//   prefix    one thread per depth-(H-1) node: float64 walk of the shared prefix, then a
+//             loop over the S children with the per-control displacement table in shared
+//             memory (no MUFU sin/cos in the inner loop: the child pose is a rotation of a
+//             tabulated displacement into the parent frame)
+#include "mpcb_types.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace mpcb {
+
+// ------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ double4 ldg_d4(const double4 *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// lexicographic (cost, index) minimum; NaN costs never win
+__device__ __forceinline__ void lex_min(double &J, long long &j, double oJ, long long oj) {
+    if (oj >= 0 && (j < 0 || oJ < J || (oJ == J && oj < j))) { J = oJ; j = oj; }
+}
+
+// The quantities one "parent" (the start pose for leafwalk, a depth-(H-1) node for prefix)
+// contributes to the cost of its leaves, in the parent's own frame.
+struct ParentRegs {
+    float u, w;        // target in the parent frame
+    float u2, w2;      // -2u, -2w
+    float D2, Dp;      // |target|^2, |target|
+    float nu, nw;      // wl * unit normal of the tracked line, parent frame
+    float e2, h2;      // 2 * wl*signed line distance of the parent, 2 * wh*(theta - phi_parent)
+};
+
+// fp32 leaf part L of the cost: J_leaf = Kbase + base_parent + L.
+//   (a, b) displacement parent->leaf in the parent frame, r = a^2+b^2, g = wh * heading change
+//   FAR : d - Dp = num / (d + Dp), num = r - 2(u a + w b)   (no cancellation; needs Dp >= 4 reach)
+//   NEAR: d - Dp = |(u - a, w - b)| - Dp                     (absolute error ~ulp(reach))
+template <bool HEAD, bool NEAR>
+__device__ __forceinline__ float leaf_val(float a, float b, float r, float g, const ParentRegs &p) {
+    float t;
+    if (NEAR) {
+        float dx = p.u - a, dy = p.w - b;
+        t = sqrt_approx(__fmaf_rn(dx, dx, dy * dy)) - p.Dp;
+    } else {
+        float num = __fmaf_rn(p.u2, a, __fmaf_rn(p.w2, b, r));
+        float d = sqrt_approx(p.D2 + num);
+        t = num * rcp_approx(d + p.Dp);
+    }
+    float q = __fmaf_rn(p.nu, a, p.nw * b);
+    float acc = q * (p.e2 + q);
+    if (HEAD) acc = __fmaf_rn(g, g - p.h2, acc);
+    return __fmaf_rn(10000.0f, t, acc);
+}
+
+__device__ __forceinline__ void start_as_parent(const SolveParams &P, ParentRegs &pr) {
+    pr.u = (float)P.u0; pr.w = (float)P.w0;
+    pr.u2 = (float)(-2.0 * P.u0); pr.w2 = (float)(-2.0 * P.w0);
+    pr.D2 = (float)(P.d0 * P.d0); pr.Dp = (float)P.d0;
+    pr.nu = (float)P.nx0; pr.nw = (float)P.ny0;
+    pr.e2 = (float)(2.0 * P.e0); pr.h2 = (float)(2.0 * P.hp0);
+}
+
+// float64 walk of the prefix (i_0 .. i_{H-2}) of depth-(H-1) node p in the start frame, then the
+// node's frame quantities.  Returns base_p (float64) and whether the node has not moved at all.
+__device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
+                                               unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved) {
+    double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
+    unsigned long long rem = p;
+    const int D = a.H - 1;
+    for (int k = 0; k < D; ++k) {
+        unsigned long long i = a.fd[k + 1].div(rem);
+        rem -= i * a.fd[k + 1].d;
+        double4 t = ldg_d4(a.g.tab64 + i);
+        double cn = cp * t.x - sp * t.y;
+        double sn = sp * t.x + cp * t.y;
+        cp = cn; sp = sn;
+        xi = fma(t.z, cp, xi);
+        eta = fma(t.z, sp, eta);
+        psi += t.w;
+    }
+    unmoved = (xi == 0.0 && eta == 0.0);
+    double relx = P.u0 - xi, rely = P.w0 - eta;
+    double u = cp * relx + sp * rely, w = cp * rely - sp * relx;
+    double D2 = u * u + w * w, Dp = sqrt(D2);
+    double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
+    double nu = cp * P.nx0 + sp * P.ny0, nw = cp * P.ny0 - sp * P.nx0;
+    double hp = P.hp0 - P.wh * psi;
+    pr.u = (float)u; pr.w = (float)w;
+    pr.u2 = (float)(-2.0 * u); pr.w2 = (float)(-2.0 * w);
+    pr.D2 = (float)D2; pr.Dp = (float)Dp;
+    pr.nu = (float)nu; pr.nw = (float)nw;
+    pr.e2 = (float)(2.0 * ep); pr.h2 = (float)(2.0 * hp);
+    near = !(Dp >= 4.0 * a.g.smax);
+    return kWd * (Dp - P.d0) + ep * ep + hp * hp;
+}
+
+// float64 cost of leaf j by the reference's own formula and operation order
+// (iteration_of_predict math_model.py:110-114, control_criterion :82-86 / tree :82-87).
+// Optionally returns the poses after each step.
+__device__ __noinline__ double exact_cost(const LaunchArgs &a, const SolveParams &P, long long j,
+                                          double *traj /* [H][3] or null */, int *first_c) {
+    const bool slow = (P.flags & kFlagSlow) != 0;
+    const double4 *tab = slow ? a.g.tab64_slow : a.g.tab64;
+    const double *vt = slow ? a.g.vtab_slow : a.g.vtab;
+    double x = P.xs, y = P.ys, phi = P.phi0;
+    unsigned long long rem = (unsigned long long)j;
+    for (int k = 0; k < a.H; ++k) {
+        unsigned long long c;
+        if (a.mode == 1) c = (unsigned long long)j;
+        else { c = a.fd[k].div(rem); rem -= c * a.fd[k].d; }
+        if (k == 0 && first_c) *first_c = (int)c;
+        double dphi = __ldg(&tab[c].w);
+        double v = __ldg(&vt[c]);
+        phi = __dadd_rn(phi, dphi);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        x = __dadd_rn(x, __dmul_rn(__dmul_rn(v, cs), a.g.dt));
+        y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, sn), a.g.dt));
+        if (traj) { traj[3 * k] = x; traj[3 * k + 1] = y; traj[3 * k + 2] = phi; }
+    }
+    double dx = P.xt - x, dy = P.yt - y;
+    double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    double dl;
+    if (x == P.ox && y == P.oy) dl = 1000.0;
+    else
+        dl = fabs(__dadd_rn(__dadd_rn(__dmul_rn(P.lineA, x), -__dmul_rn(P.lineB, y)), P.lineC)) / P.line_norm;
+    double dl2 = __dmul_rn(dl, dl);
+    if (a.cost_kind == 0) {
+        double ang = P.theta - phi;
+        return __dadd_rn(__dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10.0, __dmul_rn(ang, ang))),
+                         __dmul_rn(100.0, dl2));
+    }
+    return __dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10000.0, dl2));
+}
+
+// candidate found by the refinement filter: evaluate and fold into the thread's running best
+__device__ __forceinline__ void take_candidate(const LaunchArgs &a, const SolveParams &P, long long j,
+                                               double jrel32, double &bJ, long long &bj) {
+    atomicAdd(a.counters + 1, 1ULL);
+    double J = a.refine ? exact_cost(a, P, j, nullptr, nullptr) : (P.Kbase + jrel32);
+    lex_min(bJ, bj, J, j);
+}
+
+// block-wide lexicographic min, then one locked update of the solve's record
+__device__ __forceinline__ void publish_best(const LaunchArgs &a, long long n, double bJ, long long bj,
+                                             double *s_J, long long *s_j) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double oJ = __shfl_xor_sync(0xffffffffu, bJ, o);
+        long long oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        lex_min(bJ, bj, oJ, oj);
+    }
+    if (lane == 0) { s_J[warp] = bJ; s_j[warp] = bj; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kThreads / 32; ++i) lex_min(bJ, bj, s_J[i], s_j[i]);
+        if (bj >= 0) {
+            while (atomicCAS(a.lock + n, 0, 1) != 0) {}
+            __threadfence();
+            double cJ = *(volatile double *)(a.bestJ + n);
+            long long cj = *(volatile long long *)(a.bestIdx + n);
+            lex_min(cJ, cj, bJ, bj);
+            *(volatile double *)(a.bestJ + n) = cJ;
+            *(volatile long long *)(a.bestIdx + n) = cj;
+            __threadfence();
+            atomicExch(a.lock + n, 0);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void publish_segmin(const LaunchArgs &a, unsigned seg, double v, double *s_J) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_min(v);
+    if (lane == 0) s_J[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double x = lane < kThreads / 32 ? s_J[lane] : INFINITY;
+        x = warp_min(x);
+        if (lane == 0) a.segmin[seg] = x;
+    }
+    __syncthreads();
+}
+
+// work item -> (segment, solve, tile range).  PASS 1 walks all segments, PASS 2 the work list.
+template <int PASS>
+__device__ __forceinline__ void decode_work(const LaunchArgs &a, unsigned long long w, unsigned &seg,
+                                            long long &n, unsigned long long &tile_lo, unsigned long long &tile_hi) {
+    const unsigned sps = (unsigned)a.segs_per_solve;
+    unsigned long long off;
+    if (PASS == 1) { seg = (unsigned)w; off = 0; }
+    else {
+        unsigned long long e = a.tps == 1 ? w : w / a.tps;
+        seg = a.worklist[e];
+        off = w - e * a.tps;
+    }
+    unsigned nn = seg / sps;
+    unsigned sidx = seg - nn * sps;
+    n = nn;
+    tile_lo = (unsigned long long)sidx * a.tps + off;
+    tile_hi = tile_lo + (PASS == 1 ? a.tps : 1);
+    if (tile_hi > a.tiles_per_solve) tile_hi = a.tiles_per_solve;
+}
+
+// ------------------------------------------------------------------------------------ prefix
+// One thread per depth-(H-1) node; the S children are scored from the shared-memory table.
+template <bool HEAD, bool NEAR>
+__device__ __forceinline__ float prefix_min_loop(const float4 *__restrict__ tab, int n, const ParentRegs &pr, float best) {
+#pragma unroll 8
+    for (int c = 0; c < n; ++c) {
+        float4 t = tab[c];
+        best = fminf(best, leaf_val<HEAD, NEAR>(t.x, t.y, t.z, t.w, pr));
+    }
+    return best;
+}
+
+template <int PASS, bool HEAD>
+__global__ void __launch_bounds__(kThreads) prefix_kernel(const LaunchArgs a) {
+    extern __shared__ float4 s_leaf[];
+    __shared__ double s_J[kThreads / 32];
+    __shared__ long long s_j[kThreads / 32];
+    const int tid = threadIdx.x;
+    const int S = a.g.S;
+    const bool single = S <= kLeafChunk;
+    if (single) {
+        for (int i = tid; i < S; i += kThreads) s_leaf[i] = __ldg(a.g.leaf32 + i);
+        __syncthreads();
+    }
+    const unsigned long long nwork =
+        PASS == 1 ? a.total_segs : (unsigned long long)(*a.work_count) * a.tps;
+    for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
+        decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
+        const SolveParams &P = a.sp[n];
+        const bool origin_case = (P.flags & kFlagStartIsOrigin) != 0;
+        const double tau = PASS == 2 ? a.tau[n] : 0.0;
+        if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
+        double segbest = INFINITY;
+        double bJ = INFINITY; long long bj = -1;
+        for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
+            const unsigned long long p = a.u_begin + tile * kThreads + tid;
+            const bool active = p < a.u_end;
+            ParentRegs pr = {};
+            bool near = false, unmoved = false;
+            double base = 0.0;
+            if (active) base = parent_setup(a, P, p, pr, near, unmoved);
+            const bool special = active && origin_case && unmoved;
+            float best = INFINITY;
+            const float thr = PASS == 2 ? __double2float_ru(tau - base) : 0.f;
+            const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+            for (int c0 = 0; c0 < S; c0 += kLeafChunk) {
+                const int cn = min(kLeafChunk, S - c0);
+                if (!single) {
+                    __syncthreads();
+                    for (int i = tid; i < cn; i += kThreads) s_leaf[i] = __ldg(a.g.leaf32 + c0 + i);
+                    __syncthreads();
+                }
+                if (!active) continue;
+                if (PASS == 1 && !special) {
+                    best = near ? prefix_min_loop<HEAD, true>(s_leaf, cn, pr, best)
+                                : prefix_min_loop<HEAD, false>(s_leaf, cn, pr, best);
+                } else {
+                    // refinement pass, or a node sitting exactly on the line origin (rare)
+                    for (int c = 0; c < cn; ++c) {
+                        float4 t = s_leaf[c];
+                        float L = near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
+                                       : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
+                        if (special && t.z == 0.f) L = Lspecial;
+                        if (PASS == 1) best = fminf(best, L);
+                        else if (L <= thr)
+                            take_candidate(a, P, (long long)(p * (unsigned long long)S + c0 + c),
+                                           base + (double)L, bJ, bj);
+                    }
+                }
+            }
+            if (PASS == 1 && active) segbest = fmin(segbest, base + (double)best);
+        }
+        if (PASS == 1) publish_segmin(a, seg, segbest, s_J);
+        else publish_best(a, n, bJ, bj, s_J, s_j);
+    }
+}
+
+// ------------------------------------------------------------------------------------ leafwalk
+// One thread per leaf: decode the control sequence, walk H steps in registers in the start frame
+// (heading relative to the start heading, so sin.approx/cos.approx see |psi| <~ 1), score.
+template <bool HEAD>
+__device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveParams &P, const ParentRegs &pr,
+                                               const float2 *__restrict__ ctl, unsigned long long j,
+                                               float &xi, float &eta, float &psi) {
+    xi = 0.f; eta = 0.f; psi = 0.f;
+    unsigned long long rem = j;
+    for (int k = 0; k < a.H; ++k) {
+        unsigned long long c;
+        if (a.mode == 1) c = j;
+        else { c = a.fd[k].div(rem); rem -= c * a.fd[k].d; }
+        float2 t = __ldg(ctl + c);
+        psi += t.x;
+        float sn, cs;
+        __sincosf(psi, &sn, &cs);
+        xi = __fmaf_rn(t.y, cs, xi);
+        eta = __fmaf_rn(t.y, sn, eta);
+    }
+    const float r = __fmaf_rn(xi, xi, eta * eta);
+    const float g = 3.16227766016837952f * psi;
+    float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
+                                    : leaf_val<HEAD, false>(xi, eta, r, g, pr);
+    if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
+        L = (float)(P.special - P.e0 * P.e0) + (HEAD ? g * (g - pr.h2) : 0.f);
+    return L;
+}
+
+template <int PASS, bool HEAD>
+__global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) {
+    __shared__ double s_J[kThreads / 32];
+    __shared__ long long s_j[kThreads / 32];
+    const int tid = threadIdx.x;
+    const unsigned long long nwork =
+        PASS == 1 ? a.total_segs : (unsigned long long)(*a.work_count) * a.tps;
+    for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
+        decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
+        const SolveParams &P = a.sp[n];
+        ParentRegs pr;
+        start_as_parent(P, pr);
+        const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
+        const float thr = PASS == 2 ? __double2float_ru(a.tau[n]) : 0.f;
+        if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
+        float best = INFINITY;
+        double bJ = INFINITY; long long bj = -1;
+        for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
+            const unsigned long long j = a.u_begin + tile * kThreads + tid;
+            if (j >= a.u_end) continue;
+            float xi, eta, psi;
+            const float L = leafwalk_eval<HEAD>(a, P, pr, ctl, j, xi, eta, psi);
+            if (PASS == 1) best = fminf(best, L);
+            else if (L <= thr) take_candidate(a, P, (long long)j, (double)L, bJ, bj);
+        }
+        if (PASS == 1) publish_segmin(a, seg, (double)best, s_J);
+        else publish_best(a, n, bJ, bj, s_J, s_j);
+    }
+}
+
+// ------------------------------------------------------------------------------------ dump
+// All leaves of solve 0 in [dump_begin, dump_begin+dump_count): {x, y, phi, L} as one 16-byte
+// store per thread (consecutive threads -> consecutive leaves: fully coalesced STG.128).
+template <bool HEAD>
+__global__ void __launch_bounds__(kThreads) leafwalk_dump_kernel(const LaunchArgs a, double *jrel) {
+    const SolveParams &P = a.sp[0];
+    ParentRegs pr;
+    start_as_parent(P, pr);
+    const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
+    const float c0 = (float)cos(P.phi0), s0 = (float)sin(P.phi0);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < a.dump_count;
+         i += (unsigned long long)gridDim.x * kThreads) {
+        float xi, eta, psi;
+        const float L = leafwalk_eval<HEAD>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi);
+        a.dump[i] = make_float4((float)P.xs + (c0 * xi - s0 * eta), (float)P.ys + (s0 * xi + c0 * eta),
+                                (float)P.phi0 + psi, L);
+        jrel[i] = (double)L;
+    }
+}
+
+// prefix flavour of the dump (test-only: strided stores): J_rel = base_p + L for every child
+template <bool HEAD>
+__global__ void __launch_bounds__(kThreads) prefix_dump_kernel(const LaunchArgs a, double *jrel) {
+    const SolveParams &P = a.sp[0];
+    const int S = a.g.S;
+    const unsigned long long p_lo = a.dump_begin / S, p_hi = (a.dump_begin + a.dump_count + S - 1) / S;
+    for (unsigned long long p = p_lo + blockIdx.x * (unsigned long long)kThreads + threadIdx.x; p < p_hi;
+         p += (unsigned long long)gridDim.x * kThreads) {
+        ParentRegs pr;
+        bool near, unmoved;
+        const double base = parent_setup(a, P, p, pr, near, unmoved);
+        const bool special = (P.flags & kFlagStartIsOrigin) && unmoved;
+        const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+        for (int c = 0; c < S; ++c) {
+            const unsigned long long j = p * S + c;
+            if (j < a.dump_begin || j >= a.dump_begin + a.dump_count) continue;
+            float4 t = __ldg(a.g.leaf32 + c);
+            float L = near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
+                           : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
+            if (special && t.z == 0.f) L = Lspecial;
+            jrel[j - a.dump_begin] = base + (double)L;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ small kernels
+// Raw inputs -> SolveParams (float64), incl. the per-solve error window of the refinement pass.
+__global__ void prep_kernel(long long N, const double *__restrict__ state, const double *__restrict__ target,
+                            const double *__restrict__ origin, const double *__restrict__ threshold,
+                            const uint8_t *__restrict__ flags, int cost_kind, int H, int prefix,
+                            double smax, double dphimax, double tol_scale, SolveParams *__restrict__ out) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    SolveParams P;
+    P.xs = state[3 * n]; P.ys = state[3 * n + 1]; P.phi0 = state[3 * n + 2];
+    P.xt = target[2 * n]; P.yt = target[2 * n + 1];
+    P.ox = origin[2 * n]; P.oy = origin[2 * n + 1];
+    P.theta = atan(P.xt / P.yt);
+    P.lineA = P.yt - P.oy; P.lineB = P.xt - P.ox;
+    P.lineC = P.xt * P.oy - P.yt * P.ox;
+    P.line_norm = sqrt(P.lineA * P.lineA + P.lineB * P.lineB);
+    P.threshold = threshold ? threshold[n] : INFINITY;
+    P.wl = cost_kind == 0 ? 10.0 : 100.0;
+    P.wh = cost_kind == 0 ? 3.16227766016837952 : 0.0;
+    double s0, c0;
+    sincos(P.phi0, &s0, &c0);
+    const double rx = P.xt - P.xs, ry = P.yt - P.ys;
+    P.u0 = c0 * rx + s0 * ry; P.w0 = c0 * ry - s0 * rx;
+    P.d0 = sqrt(rx * rx + ry * ry);
+    const double E0 = P.lineA * P.xs - P.lineB * P.ys + P.lineC;
+    P.e0 = P.wl * E0 / P.line_norm;
+    P.nx0 = P.wl * (P.lineA * c0 - P.lineB * s0) / P.line_norm;
+    P.ny0 = P.wl * (-P.lineA * s0 - P.lineB * c0) / P.line_norm;
+    P.hp0 = P.wh * (P.theta - P.phi0);
+    P.Kbase = kWd * P.d0;
+    P.special = 1.0e6 * P.wl * P.wl;
+    int f = flags ? (flags[n] & kFlagSlow) : 0;
+    if (P.xs == P.ox && P.ys == P.oy) f |= kFlagStartIsOrigin;
+    // error model of the fp32 leaf part
+    const double Rtot = H * smax;
+    const double Rl = prefix ? smax : Rtot;
+    const double Gl = P.wh * (prefix ? dphimax : H * dphimax);
+    const bool near = !(P.d0 >= 4.0 * Rl);
+    if (!prefix && near) f |= kFlagNear;
+    const double E = fabs(P.e0) + P.wl * Rtot, Hh = fabs(P.hp0) + P.wh * H * dphimax, Q = P.wl * Rl;
+    double M = kWd * Rl * 16.0 + 4.0 * Q * (2.0 * E + Q) + 4.0 * Gl * (Gl + 2.0 * Hh);
+    if (!prefix) M += kWd * Rtot * 8.0;            // sin.approx / cos.approx absolute error per step
+    P.tol = 2.0 * M * 1.1920928955078125e-07 * tol_scale;
+    P.flags = f; P.pad = 0;
+    out[n] = P;
+}
+
+// Per solve: minimum of its segment minima -> window edge tau; segments inside the window -> work list.
+__global__ void __launch_bounds__(kThreads) reduce_compact_kernel(const LaunchArgs a, double *tau,
+                                                                  unsigned *worklist, unsigned *work_count) {
+    __shared__ double s_J[kThreads / 32];
+    __shared__ double s_tau;
+    const unsigned sps = (unsigned)a.segs_per_solve;
+    for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
+        const double *sm = a.segmin + (unsigned long long)n * sps;
+        double v = INFINITY;
+        for (unsigned i = threadIdx.x; i < sps; i += kThreads) v = fmin(v, sm[i]);
+        v = warp_min(v);
+        if ((threadIdx.x & 31) == 0) s_J[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < kThreads / 32; ++i) v = fmin(v, s_J[i]);
+            const double t = v + (a.refine ? a.sp[n].tol : 0.0);
+            s_tau = t;
+            tau[n] = t;
+            a.bestJ[n] = INFINITY;
+            a.bestIdx[n] = -1;
+            a.lock[n] = 0;
+        }
+        __syncthreads();
+        const double t = s_tau;
+        if (t < INFINITY)
+            for (unsigned i = threadIdx.x; i < sps; i += kThreads)
+                if (sm[i] <= t) worklist[atomicAdd(work_count, 1u)] = (unsigned)(n * sps + i);
+        __syncthreads();
+    }
+}
+
+// Winner -> outputs: float64 re-roll of its trajectory, threshold test (math_model.py:195).
+__global__ void finalize_kernel(const LaunchArgs a, double *best_cost, long long *best_index, double *best_traj,
+                                double *first_control) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    const SolveParams &P = a.sp[n];
+    const long long j = a.bestIdx[n];
+    double J = a.bestJ[n];
+    double tr[3 * kMaxH];
+    int c0 = 0;
+    bool ok = j >= 0;
+    if (ok) {
+        const double Je = exact_cost(a, P, j, tr, &c0);
+        if (a.refine) J = Je;
+    } else {
+        J = NAN;
+    }
+    if (best_cost) best_cost[n] = J;
+    if (best_index) best_index[n] = (ok && J < P.threshold) ? j : -1;
+    if (best_traj)
+        for (int k = 0; k < 3 * a.H; ++k) best_traj[(size_t)n * 3 * a.H + k] = ok ? tr[k] : NAN;
+    if (first_control) {
+        const bool slow = (P.flags & kFlagSlow) != 0;
+        first_control[2 * n] = ok ? (slow ? a.g.vtab_slow : a.g.vtab)[c0] : NAN;
+        first_control[2 * n + 1] = ok ? a.g.beta[c0 % a.g.nb] : NAN;
+    }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+static inline int grid_for(unsigned long long work, int sms, int per_sm) {
+    unsigned long long cap = (unsigned long long)sms * per_sm;
+    return (int)(work < cap ? (work ? work : 1) : cap);
+}
+
+cudaError_t launch_prep(cudaStream_t st, long long N, const double *state, const double *target,
+                        const double *origin, const double *threshold, const uint8_t *flags, int cost_kind, int H,
+                        int prefix, double smax, double dphimax, double tol_scale, SolveParams *out) {
+    const int bs = 128;
+    prep_kernel<<<(unsigned)((N + bs - 1) / bs), bs, 0, st>>>(N, state, target, origin, threshold, flags, cost_kind,
+                                                            H, prefix, smax, dphimax, tol_scale, out);
+    return cudaGetLastError();
+}
+
+static size_t prefix_smem(const LaunchArgs &a) {
+    return sizeof(float4) * (size_t)(a.g.S < kLeafChunk ? a.g.S : kLeafChunk);
+}
+
+template <typename K>
+static int resident_ctas(K kernel, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+template <typename K>
+static cudaError_t launch_persistent(K kernel, const LaunchArgs &a, int pass, size_t smem, int sms, cudaStream_t st) {
+    // pass 1: one CTA per resident slot, striding over the segments; pass 2: same grid over the
+    // device-side work list (its length is not known on the host)
+    const int slots = sms * resident_ctas(kernel, smem);
+    const int grid = pass == 1 ? (int)(a.total_segs < (unsigned long long)slots ? a.total_segs : slots) : slots;
+    kernel<<<grid, kThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool prefix, int sms) {
+    const bool head = a.cost_kind == 0;
+    if (prefix) {
+        const size_t sm = prefix_smem(a);
+        if (pass == 1)
+            return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st)
+                        : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st);
+        return head ? launch_persistent(prefix_kernel<2, true>, a, pass, sm, sms, st)
+                    : launch_persistent(prefix_kernel<2, false>, a, pass, sm, sms, st);
+    }
+    if (pass == 1)
+        return head ? launch_persistent(leafwalk_kernel<1, true>, a, pass, 0, sms, st)
+                    : launch_persistent(leafwalk_kernel<1, false>, a, pass, 0, sms, st);
+    return head ? launch_persistent(leafwalk_kernel<2, true>, a, pass, 0, sms, st)
+                : launch_persistent(leafwalk_kernel<2, false>, a, pass, 0, sms, st);
+}
+
+cudaError_t launch_reduce_compact(cudaStream_t st, const LaunchArgs &a, double *tau, unsigned *worklist,
+                                  unsigned *work_count, int sms) {
+    reduce_compact_kernel<<<grid_for((unsigned long long)a.N, sms, 8), kThreads, 0, st>>>(a, tau, worklist,
+                                                                                         work_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(cudaStream_t st, const LaunchArgs &a, double *best_cost, long long *best_index,
+                            double *best_traj, double *first_control) {
+    const int bs = 128;
+    finalize_kernel<<<(unsigned)((a.N + bs - 1) / bs), bs, 0, st>>>(a, best_cost, best_index, best_traj,
+                                                                  first_control);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dump(cudaStream_t st, const LaunchArgs &a, bool prefix, double *jrel, int sms) {
+    const bool head = a.cost_kind == 0;
+    if (prefix) {
+        const unsigned long long parents = a.dump_count / a.g.S + 2;
+        const int grid = grid_for((parents + kThreads - 1) / kThreads, sms, 8);
+        if (head) prefix_dump_kernel<true><<<grid, kThreads, 0, st>>>(a, jrel);
+        else prefix_dump_kernel<false><<<grid, kThreads, 0, st>>>(a, jrel);
+    } else {
+        const int grid = grid_for((a.dump_count + kThreads - 1) / kThreads, sms, 8);
+        if (head) leafwalk_dump_kernel<true><<<grid, kThreads, 0, st>>>(a, jrel);
+        else leafwalk_dump_kernel<false><<<grid, kThreads, 0, st>>>(a, jrel);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mpcb

@@ -1,0 +1,94 @@
+// mpcb_types.cuh -- device-side data layout shared by the kernels and the host API.
+//
+// Everything a kernel needs lives in three places:
+//   GridTables   per control grid, built once by mpcb_set_grid (read-only, L2/L1 resident)
+//   SolveParams  one 256-byte record per MPC solve, built on the device by prep_kernel
+//   LaunchArgs   per launch, passed by value (constant bank)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mpcb {
+
+constexpr int kThreads = 256;      // threads per CTA; one "unit" (leaf or depth-(H-1) node) per thread
+constexpr int kMaxH = 8;
+constexpr int kLeafChunk = 1024;   // float4 entries of the per-control leaf table staged in shared memory
+
+// cost weights (math_model.py:86 / math_model_tree.py:87)
+constexpr double kWd = 10000.0;
+
+// Division of a 64-bit index by an invariant divisor (Granlund-Montgomery round-up form).
+struct FastDiv64 {
+    unsigned long long m;   // magic
+    unsigned long long d;   // divisor
+    unsigned sh1, sh2;
+#ifdef __CUDACC__
+    __device__ __forceinline__ unsigned long long div(unsigned long long n) const {
+        unsigned long long t = __umul64hi(m, n);
+        return (t + ((n - t) >> sh1)) >> sh2;
+    }
+#endif
+};
+
+// Per control grid. c = iv*nb + ib.
+struct GridTables {
+    // float64, for the depth-(H-1) prefix walk and the exact re-evaluation
+    const double4 *tab64;       // {cos dphi_c, sin dphi_c, s_c = v_c*dt, dphi_c}
+    const double  *vtab;        // v_c
+    const double4 *tab64_slow;  // same with every v := max(min V, v_min)   (math_model_tree.py:312-316)
+    const double  *vtab_slow;
+    const double  *beta;        // beta[nb]
+    // float32, for the inner loops
+    const float4 *leaf32;       // {a_c = s_c cos dphi_c, b_c = s_c sin dphi_c, r_c = s_c^2, g_c = sqrt(10) dphi_c}
+    const float2 *ctl32;        // {dphi_c, s_c}
+    const float2 *ctl32_slow;
+    int S, nb;
+    double dt;
+    double smax, dphimax;       // max s_c, max |dphi_c| (both variants) -- error model
+};
+
+// Per solve (float64). Built by prep_kernel from the raw inputs.
+struct __align__(16) SolveParams {
+    double xs, ys, phi0;        // start pose
+    double xt, yt;              // target
+    double ox, oy;              // origin of the tracked line
+    double theta;               // arctan(x_t / y_t)                         (math_model.py:83)
+    double lineA, lineB, lineC, line_norm;   // (y_t-y_0), (x_t-x_0), x_t y_0 - y_t x_0, sqrt(A^2+B^2)
+    double threshold;
+    // start-frame quantities (frame: origin at the start position, x axis along the start heading)
+    double u0, w0, d0;          // target, distance to target
+    double e0, nx0, ny0;        // wl * signed line distance of the start, and its gradient
+    double hp0;                 // wh * (theta - phi0)
+    double wl, wh;              // sqrt of the line / heading weights
+    double Kbase;               // kWd * d0 : J = Kbase + J_rel
+    double tol;                 // half-width of the candidate window of the refinement pass
+    double special;             // 1e6 * wl^2: squared line term of the "on the origin" special case
+    int flags;                  // bit0 slow, bit1 start_is_origin, bit2 near (leafwalk regime)
+    int pad;
+};
+constexpr int kFlagSlow = 1, kFlagStartIsOrigin = 2, kFlagNear = 4;
+
+struct LaunchArgs {
+    GridTables g;
+    const SolveParams *sp;
+    FastDiv64 fd[kMaxH];        // fd[k].d = S^(H-1-k)
+    int mode, H, cost_kind, refine;
+    long long N;
+    unsigned long long u_begin, u_end;     // unit range of every solve (leaves or depth-(H-1) nodes)
+    unsigned long long tiles_per_solve, segs_per_solve, total_segs;
+    unsigned tps;                          // tiles per segment
+    double *segmin;                        // [total_segs]  pass-1 partial minima of J_rel
+    // refinement
+    const unsigned *worklist;              // qualifying segment ids
+    const unsigned *work_count;
+    double *bestJ;                         // [N] exact cost of the best candidate so far
+    long long *bestIdx;                    // [N]
+    int *lock;                             // [N]
+    unsigned long long *counters;          // [0] refine segments, [1] candidates
+    const double *tau;                     // [N] J_rel window upper edge
+    // dump
+    float4 *dump;                          // {x, y, phi, J_rel} per leaf
+    unsigned long long dump_begin, dump_count;
+};
+
+}  // namespace mpcb

@@ -1,0 +1,152 @@
+/* mpcb200.h -- C ABI of the B200-native MPC inner loop (libmpcb200.so).
+ *
+ * Drop-in boundary for ONE path of ShittyWizard/DiplomJourney: expansion of the
+ * control-input tree over the horizon, kinematic-bicycle rollout of every
+ * candidate control sequence, terminal tracking cost, first-minimum argmin.
+ * The reference has no FFI of its own; the functions below replace the bodies
+ * of the Python functions cited on each entry (paths are into the reference
+ * repository).  Plain C: pointers + sizes, no torch types, no exceptions.
+ *
+ * Conventions
+ *   - every function returns 0 (MPCB_OK) or a negative mpcb_status; the text
+ *     of the last error of a handle is available from mpcb_last_error().
+ *   - control c = iv*nb + ib (velocity outer loop, angle inner loop:
+ *     math_model.py:163-164).  S = nv*nb controls per step.
+ *   - FULL leaf index  j = sum_k i_k * S^(H-1-k), i_0 = first applied control
+ *     (math_model.py:159-200).  HELD leaf index k in [0,S): control k held for
+ *     all H steps (math_model_tree.py:308-361, CoordinateTree.py:20-30).
+ *   - ties resolve to the lowest leaf index (strict '<', math_model.py:195).
+ *   - a handle owns one device, one stream and its scratch; it is not
+ *     thread-safe, distinct handles are independent.
+ *   - "_host" entry points take host pointers and copy; "_device" entry points
+ *     take device pointers valid on the handle's device and enqueue on the
+ *     handle's stream without synchronising (call mpcb_sync).
+ *   - there is no CPU fallback: without a CUDA device mpcb_create fails.
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MPCB_API __attribute__((visibility("default")))
+#else
+#define MPCB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpcb_handle_s mpcb_handle;
+
+typedef enum {
+    MPCB_OK = 0,
+    MPCB_ERR_INVALID = -1,      /* bad argument (null pointer, H out of range, ...) */
+    MPCB_ERR_CUDA = -2,         /* CUDA runtime error, see mpcb_last_error */
+    MPCB_ERR_NO_GRID = -3,      /* solve before mpcb_set_grid */
+    MPCB_ERR_EMPTY_GRID = -4,   /* nv == 0 or nb == 0 (reference: np.min([]) raises, math_model_tree.py:313) */
+    MPCB_ERR_TOO_LARGE = -5,    /* S^H does not fit in int64 */
+    MPCB_ERR_NO_DEVICE = -6,
+    MPCB_ERR_NCCL = -7
+} mpcb_status;
+
+/* tree semantics */
+#define MPCB_MODE_FULL 0 /* predictive_control, math_model.py:136-231 / run_math_model.py:133-228 */
+#define MPCB_MODE_HELD 1 /* predictive_control, math_model_tree.py:278-496 (CoordinateTree-pruned) */
+/* terminal cost */
+#define MPCB_COST_MM 0   /* control_criterion math_model.py:82-86:  1e4 d + 10 (atan(x_t/y_t)-phi)^2 + 100 d_l^2 */
+#define MPCB_COST_TREE 1 /* control_criterion math_model_tree.py:82-87: 1e4 d + 1e4 d_l^2 */
+/* expansion algorithm (FULL only; HELD always walks one thread per leaf) */
+#define MPCB_ALGO_AUTO 0
+#define MPCB_ALGO_LEAFWALK 1 /* one thread per leaf walks the whole horizon (2H+1 MUFU per rollout) */
+#define MPCB_ALGO_PREFIX 2   /* one thread per depth-(H-1) node, loops its S children (prefix sharing) */
+
+#define MPCB_MAX_H 8
+
+/* per-solve flags (uint8 per solve) */
+#define MPCB_FLAG_SLOW 1 /* steps_for_slowing > 0: every velocity := max(min(V), v_min), math_model_tree.py:312-316 */
+
+MPCB_API int mpcb_version(void);
+MPCB_API int mpcb_device_count(void);
+
+MPCB_API int mpcb_create(int device_ordinal, mpcb_handle **out);
+MPCB_API int mpcb_destroy(mpcb_handle *h);
+MPCB_API const char *mpcb_last_error(const mpcb_handle *h);
+/* the CUDA stream (cudaStream_t) the handle enqueues on, as an opaque pointer */
+MPCB_API void *mpcb_stream(mpcb_handle *h);
+MPCB_API int mpcb_sync(mpcb_handle *h);
+
+/* Control grid + vehicle constants.  Replaces the module-level grids
+ * (math_model.py:23-30) / the per-tick windows handed to predictive_control
+ * (math_model_tree.py:543-551) and builds the per-control tables
+ * dphi_c = (v_c/L) tan(beta_c) delta_t, s_c = v_c delta_t   (math_model.py:69-78,90-114). */
+MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, int nb,
+                  double L, double delta_t, double v_min);
+
+/* Options: "tol_scale" (candidate-window multiplier, default 1), "algo" (MPCB_ALGO_*),
+ * "refine" (1 = float64 re-evaluation of near-minimal leaves, default; 0 = fp32 winner). */
+MPCB_API int mpcb_set_option(mpcb_handle *h, const char *name, double value);
+
+/* Batch of N independent MPC solves sharing the grid.  Replaces N calls of
+ * predictive_control (math_model.py:136 / math_model_tree.py:278).
+ *   state[N][3]   x, y, phi at the start of the solve
+ *   target[N][2]  x_t, y_t            (module globals in the reference)
+ *   origin[N][2]  x_0, y_0 of the tracked line (moves on new_target, math_model_tree.py:119-125)
+ *   threshold[N]  accept only a leaf with cost < threshold (optimal_criterion, math_model.py:195);
+ *                 NULL = +inf
+ *   flags[N]      MPCB_FLAG_*; NULL = 0
+ * outputs (any may be NULL):
+ *   best_cost[N]        float64 cost of the minimal leaf (reference formula, float64)
+ *   best_index[N]       its leaf index, or -1 if no leaf has cost < threshold (or all costs are NaN)
+ *   best_traj[N][H][3]  float64 poses after each step of the minimal leaf's sequence
+ *   first_control[N][2] (v, beta) of its first step (v after the slow-down override)
+ * Restricting FULL to first controls [i0_begin, i0_end) gives one rank's share of a
+ * split tree (indices stay global); pass 0, -1 for the whole tree. */
+MPCB_API int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
+                          const double *state, const double *target, const double *origin,
+                          const double *threshold, const uint8_t *flags,
+                          int64_t i0_begin, int64_t i0_end,
+                          double *best_cost, int64_t *best_index, double *best_traj, double *first_control);
+
+MPCB_API int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
+                            const double *state, const double *target, const double *origin,
+                            const double *threshold, const uint8_t *flags,
+                            int64_t i0_begin, int64_t i0_end,
+                            double *best_cost, int64_t *best_index, double *best_traj, double *first_control);
+
+/* Every leaf of ONE small tree in enumeration order (debug / plots / parity): the
+ * reference scatters all leaf positions (math_model.py:192-193,204).
+ *   xy[count][2] float32 terminal position, cost[count] float64 = the kernel's own fp32
+ *   evaluation of the leaf cost (offset form) re-based to the absolute cost.
+ * Host pointers. algo selects which kernel family evaluates the leaves. */
+MPCB_API int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int algo,
+                          const double *state, const double *target, const double *origin, uint8_t flags,
+                          int64_t leaf_begin, int64_t count, float *xy, double *cost);
+
+/* Statistics of the last solve on this handle (for tests and bench accounting). */
+typedef struct {
+    int64_t units;            /* leaves (leafwalk) or depth-(H-1) nodes (prefix) per solve */
+    int64_t leaves_per_solve;
+    int64_t segments;         /* pass-1 partial minima */
+    int64_t refine_segments;  /* segments re-run by the float64 refinement pass */
+    int64_t refine_candidates;/* leaves re-evaluated in float64 */
+    int32_t algo;             /* MPCB_ALGO_* actually used */
+    int32_t kernel_launches;  /* kernels enqueued by the last solve */
+} mpcb_stats;
+MPCB_API int mpcb_get_stats(mpcb_handle *h, mpcb_stats *out);
+
+/* Cross-rank reconciliation of a split tree: lexicographic (cost, index) minimum over the
+ * ranks of an NCCL communicator (two 8-byte all-reduce-min rounds, exact for float64 costs
+ * and 63-bit indices).  comm is an ncclComm_t; cost/index are device pointers (1 element). */
+MPCB_API int mpcb_allreduce_min(mpcb_handle *h, void *nccl_comm, double *cost_dev, int64_t *index_dev);
+/* NCCL bootstrap helpers (id is 128 bytes, generated on rank 0 and distributed by the caller). */
+MPCB_API int mpcb_nccl_unique_id(void *id128);
+MPCB_API int mpcb_nccl_comm_create(mpcb_handle *h, int nranks, int rank, const void *id128, void **comm_out);
+MPCB_API int mpcb_nccl_comm_destroy(void *comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H */

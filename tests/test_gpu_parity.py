@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path (through the C ABI, libmpcb200.so) against the float64 oracle and
+the golden fixtures produced by the reference's own functions.
+
+Bars: the winning leaf index is IDENTICAL to the float64 oracle's (the refinement
+pass re-evaluates near-minimal leaves in float64 with the reference's formula), cost rtol 1e-12,
+trajectory atol 1e-12.  The fp32 stage is checked separately against its own error model."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as K
+from oracle import closed_form as C
+
+pytestmark = pytest.mark.gpu
+
+nat = pytest.importorskip("diplomjourney_b200._native")
+
+MODES = {"full": nat.MODE_FULL, "held": nat.MODE_HELD}
+COSTS = {C.COST_MM: nat.COST_MM, C.COST_TREE: nat.COST_TREE}
+L, DT, VMIN = C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"]
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = nat.Solver(0)
+    yield s
+    s.close()
+
+
+def _check(res, i, ref, H):
+    assert res["index"][i] == ref["index"], (res["index"][i], ref["index"], res["cost"][i], ref["cost"])
+    assert res["cost"][i] == pytest.approx(ref["cost"], rel=1e-12)
+    np.testing.assert_allclose(res["traj"][i], ref["traj"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(res["first_control"][i], ref["first_control"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+def test_full_golden_reference_outputs(solver, golden, algo):
+    g = golden("full_h3")
+    solver.set_option("algo", algo)
+    try:
+        for case in g["cases"]:
+            sc = case["scenario"]
+            solver.set_grid(case["vector_v"], case["vector_beta"], L, DT, VMIN)
+            prev = None
+            for tick in case["ticks"]:
+                r = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, tick["state"], (sc["x_t"], sc["y_t"]),
+                                 (sc["x_0"], sc["y_0"]), threshold=tick["threshold"])
+                if r["index"][0] >= 0:
+                    ret = list(r["traj"][0, 0]) + list(r["first_control"][0])
+                    np.testing.assert_allclose(ret, tick["ret"], rtol=0, atol=1e-12)
+                    np.testing.assert_allclose(r["traj"][0], np.array(tick["traj"]), rtol=0, atol=1e-12)
+                    assert r["cost"][0] == pytest.approx(tick["criterion_after"], rel=1e-12)
+                else:  # stall: nothing beats the carried threshold, the reference repeats itself
+                    assert tick["ret"] == prev and tick["criterion_after"] == tick["threshold"]
+                prev = tick["ret"]
+    finally:
+        solver.set_option("algo", nat.ALGO_AUTO)
+
+
+def test_held_golden_reference_outputs(solver, golden):
+    g = golden("held_single")
+    for c in g["cases"]:
+        solver.set_grid(c["vector_v"], c["vector_beta"], L, DT, VMIN)
+        r = solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, c["state"], c["target"], c["origin"],
+                         flags=nat.FLAG_SLOW if c["slow"] else 0)
+        ret = list(r["traj"][0, 0]) + list(r["first_control"][0])
+        np.testing.assert_allclose(ret, c["ret"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r["traj"][0], np.array(c["traj"]), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+@pytest.mark.parametrize("H", [1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+def test_full_small_trees_vs_oracle(solver, cost, H, algo):
+    V, B = [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 7)
+    solver.set_grid(V, B, L, DT, VMIN)
+    solver.set_option("algo", algo)
+    try:
+        sc = C.random_scenarios(24, 100 + H)
+        res = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
+        for i, s in enumerate(sc):
+            _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, cost), H)
+    finally:
+        solver.set_option("algo", nat.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_fp32_stage_within_error_model(solver, algo, cost):
+    """All-leaf dump of the fp32 stage vs float64 oracle: the per-leaf error stays inside the
+    window the refinement pass assumes (P.tol/2), with margin."""
+    V, B = [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 9)
+    solver.set_grid(V, B, L, DT, VMIN)
+    H = 3
+    sc = C.random_scenarios(12, 5)
+    # plus near-target starts (NEAR regime) and off-line origins
+    near = sc[:4].copy()
+    near[:, 3] = near[:, 0] + 0.07
+    near[:, 4] = near[:, 1] - 0.05
+    worst = 0.0
+    for s, origin in [(s, s[:2]) for s in sc] + [(s, s[:2] + [0.4, -0.2]) for s in near]:
+        xy, J = solver.dump_leaves(nat.MODE_FULL, COSTS[cost], H, s[:3], s[3:5], origin, algo=algo)
+        Jo, xo, yo, _ = C.full_leaf_costs(s[:3], s[3:5], origin, V, B, H, cost, return_xy=True)
+        ok = Jo < 1e7     # the "on the origin" leaves carry 1e8/1e10 and are compared relatively
+        err = np.abs(J - Jo)
+        worst = max(worst, err[ok].max())
+        assert np.all(err[~ok] <= 1e-6 * Jo[~ok])
+        np.testing.assert_allclose(xy[:, 0], xo, atol=2e-5)
+        np.testing.assert_allclose(xy[:, 1], yo, atol=2e-5)
+    # error model (prep_kernel): eps = tol/2; measured error must stay below it
+    reach = (1 if algo == nat.ALGO_PREFIX else H) * 1.0 * DT
+    eps_model = (1e4 * reach * 16 + (0 if algo == nat.ALGO_PREFIX else 1e4 * H * DT * 8)) * 2.0 ** -23
+    assert worst < eps_model, (worst, eps_model)
+
+
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_full_default_window_grid_vs_oracle(solver, cost):
+    """S=451 (11x41 acceleration window), H=3: 9.2e7 leaves per solve, prefix kernel."""
+    V, B = C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0)
+    solver.set_grid(V, B, L, DT, VMIN)
+    sc = C.random_scenarios(6, 42)
+    res = solver.solve(nat.MODE_FULL, COSTS[cost], 3, sc[:, :3], sc[:, 3:5], sc[:, :2])
+    assert solver.stats()["algo"] == nat.ALGO_PREFIX
+    for i, s in enumerate(sc):
+        _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, 3, cost), 3)
+
+
+def test_held_full_resolution_grid_batch(solver):
+    """HELD on the FULL scripts' 201x121 grid (S=24,321) for a batch of robots, both costs."""
+    V, B = C.grid_full_default()
+    solver.set_grid(V, B, L, DT, VMIN)
+    sc = C.random_scenarios(16, 9)
+    for cost in (C.COST_MM, C.COST_TREE):
+        res = solver.solve(nat.MODE_HELD, COSTS[cost], 3, sc[:, :3], sc[:, 3:5], sc[:, :2])
+        for i, s in enumerate(sc):
+            _check(res, i, K.solve_held(s[:3], s[3:], s[:2], V, B, 3, cost), 3)
+
+
+def test_zero_velocity_exact_ties_pick_first_leaf(solver):
+    V, B = [0.0], np.linspace(-1, 1, 5)
+    solver.set_grid(V, B, L, DT, VMIN)
+    for mode in (nat.MODE_FULL, nat.MODE_HELD):
+        for origin in ((0.0, 0.0), (1.0, 2.0)):      # second: start IS the origin -> special case on every leaf
+            r = solver.solve(mode, nat.COST_MM, 3, [1.0, 2.0, 0.3], (3.0, 4.0), origin)
+            assert r["index"][0] == 0
+    # v=0 at the last step only: 5-way exact tie below one parent -> lowest beta index
+    V2 = [0.0, 1.0]
+    solver.set_grid(V2, B, L, DT, VMIN)
+    s = [0.0, 0.0, 0.0]
+    tgt = (0.1, 0.0)   # two steps at v=1 land on it; third step must stop
+    r = solver.solve(nat.MODE_FULL, nat.COST_TREE, 3, s, tgt, (-1.0, 0.0))
+    ref = K.solve_full(s, tgt, (-1.0, 0.0), V2, B, 3, C.COST_TREE)
+    assert r["index"][0] == ref["index"]
+
+
+def test_threshold_and_split_ranges(solver):
+    V, B = [0.0, 0.5, 1.0], np.linspace(-1, 1, 5)
+    solver.set_grid(V, B, L, DT, VMIN)
+    s = C.random_scenarios(1, 5)[0]
+    whole = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, s[:3], s[3:5], s[:2])
+    ref = K.solve_full(s[:3], s[3:], s[:2], V, B, 3)
+    assert whole["index"][0] == ref["index"]
+    # threshold exactly at the minimum -> strict '<' rejects (math_model.py:195)
+    r = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, s[:3], s[3:5], s[:2], threshold=whole["cost"][0])
+    assert r["index"][0] == -1 and r["cost"][0] == whole["cost"][0]
+    r = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, s[:3], s[3:5], s[:2], threshold=np.nextafter(whole["cost"][0], np.inf))
+    assert r["index"][0] == whole["index"][0]
+    # contiguous first-control shares recombine to the whole-tree answer
+    parts = [solver.solve(nat.MODE_FULL, nat.COST_MM, 3, s[:3], s[3:5], s[:2], i0_range=rg)
+             for rg in ((0, 4), (4, 9), (9, 15))]
+    for p, rg in zip(parts, ((0, 4), (4, 9), (9, 15))):
+        pr = K.solve_full(s[:3], s[3:], s[:2], V, B, 3, i0_range=rg)
+        assert p["index"][0] == pr["index"]
+    best = min(parts, key=lambda r: (r["cost"][0], r["index"][0]))
+    assert best["index"][0] == whole["index"][0]
+
+
+def test_degenerate_inputs_do_not_select_a_leaf(solver):
+    V, B = [0.0, 0.5, 1.0], np.linspace(-1, 1, 5)
+    solver.set_grid(V, B, L, DT, VMIN)
+    # target == line origin: 0/0 in the line distance -> every cost NaN -> no leaf (reference: ZeroDivisionError)
+    r = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, [0.0, 0.0, 0.0], (1.0, 1.0), (1.0, 1.0))
+    assert r["index"][0] == -1 and math.isnan(r["cost"][0])
+    with pytest.raises(nat.MpcbError):
+        solver.set_grid([], B, L, DT, VMIN)
+    with pytest.raises(nat.MpcbError):
+        solver.solve(nat.MODE_FULL, nat.COST_MM, 3, [0.0, 0.0, 0.0], (1.0, 1.0), (0.0, 0.0))  # grid was dropped
