@@ -121,7 +121,8 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     pr.nu = (float)nu; pr.nw = (float)nw;
     pr.e2 = (float)(2.0 * ep); pr.h2 = (float)(2.0 * hp);
     near = !(Dp >= 4.0 * a.g.smax);
-    return kWd * (Dp - P.d0) + ep * ep + hp * hp;
+    // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
+    return kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
 }
 
 // float64 cost of leaf j by the reference's own formula and operation order
@@ -445,7 +446,7 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     P.nx0 = P.wl * (P.lineA * c0 - P.lineB * s0) / P.line_norm;
     P.ny0 = P.wl * (-P.lineA * s0 - P.lineB * c0) / P.line_norm;
     P.hp0 = P.wh * (P.theta - P.phi0);
-    P.Kbase = kWd * P.d0;
+    P.Kbase = kWd * P.d0 + P.e0 * P.e0 + P.hp0 * P.hp0;
     P.special = 1.0e6 * P.wl * P.wl;
     int f = flags ? (flags[n] & kFlagSlow) : 0;
     if (P.xs == P.ox && P.ys == P.oy) f |= kFlagStartIsOrigin;

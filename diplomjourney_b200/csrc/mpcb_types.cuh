@@ -60,7 +60,7 @@ struct __align__(16) SolveParams {
     double e0, nx0, ny0;        // wl * signed line distance of the start, and its gradient
     double hp0;                 // wh * (theta - phi0)
     double wl, wh;              // sqrt of the line / heading weights
-    double Kbase;               // kWd * d0 : J = Kbase + J_rel
+    double Kbase;               // kWd d0 + e0^2 + hp0^2 (cost terms of the start pose): J = Kbase + J_rel
     double tol;                 // half-width of the candidate window of the refinement pass
     double special;             // 1e6 * wl^2: squared line term of the "on the origin" special case
     int flags;                  // bit0 slow, bit1 start_is_origin, bit2 near (leafwalk regime)
