@@ -1,0 +1,28 @@
+"""Test-only stand-in for diplomjourney_b200._native.Solver that answers from the float64
+oracle.  It lets the CPU suite exercise the HOST logic of the reference-API modules (closed loop,
+operator events, finishing heuristic, logs) without a GPU.  Never used by the product."""
+import numpy as np
+
+from oracle import closed_form as C
+
+
+class OracleBackend:
+    def __init__(self):
+        self.grid = None
+        self.calls = 0
+
+    def set_grid(self, vector_v, vector_beta, L, delta_t, v_min=0.0):
+        self.grid = (list(vector_v), list(vector_beta), L, delta_t, v_min)
+
+    def solve(self, mode, cost, H, state, target, origin, threshold=None, flags=None, i0_range=None):
+        V, B, L, dt, v_min = self.grid
+        self.calls += 1
+        thr = np.inf if threshold is None else float(threshold)
+        ck = C.COST_MM if cost == 0 else C.COST_TREE
+        if mode == 1:
+            r = C.solve_held(state, target, origin, V, B, H, ck, threshold=thr, slow=bool(flags), v_min=v_min,
+                             L=L, delta_t=dt)
+        else:
+            r = C.solve_full(state, target, origin, V, B, H, ck, threshold=thr, L=L, delta_t=dt, i0_range=i0_range)
+        return dict(cost=np.array([r["cost"]]), index=np.array([r["index"]]), traj=r["traj"][None],
+                    first_control=np.array([r["first_control"]]))

@@ -1,0 +1,62 @@
+"""The C-ABI library: builds with nvcc for sm_100a, loads, and exports every symbol that
+include/mpcb200.h declares.  No compute calls here (no GPU in the CPU suite)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mpcb200.h")).read()
+    return re.findall(r"MPCB_API\s+[\w\s\*]+?\b(mpcb_\w+)\s*\(", src)
+
+
+def test_header_is_plain_c():
+    # the boundary is C: the header must compile as C11 with no CUDA/torch headers
+    r = subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "mpcb200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from diplomjourney_b200 import _native, build
+    path = build.build_library()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 17 and "mpcb_solve_batch_host" in names and "mpcb_allreduce_min" in names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert _native.load().mpcb_version() >= 100
+
+
+def test_sm100a_code_is_in_the_library():
+    from diplomjourney_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.build_library()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device the product path must fail loudly, not answer from the CPU."""
+    from diplomjourney_b200 import _native
+    if _native.load().mpcb_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_native.MpcbError):
+        _native.Solver(0)
+    from diplomjourney_b200 import math_model_tree as mt
+    mt._backend = None
+    with pytest.raises(_native.MpcbError):
+        mt.predictive_control(0.0, 0.0, 0.0, 2, 3, [0.5], [0.0], False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "diplomjourney_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", txt, re.M), f
