@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib", "libmpcb200.so")
+LIB = os.environ.get("MPCB_LIB") or os.path.join(HERE, "lib", "libmpcb200.so")   # MPCB_LIB: developer override
 SOURCES = ["mpcb_kernels.cu", "mpcb_api.cu", "mpcb_nccl.cu"]
 HEADERS = ["mpcb_types.cuh", os.path.join("..", "..", "include", "mpcb200.h")]
 NVCC_FLAGS = [
@@ -37,18 +37,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    out = out or LIB
+    if not force and out == LIB and not needs_build():
         return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-ldl"]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -64,7 +64,7 @@ struct mpcb_handle_s {
     // grid
     bool have_grid = false;
     GridTables g{};
-    DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, ctl32, ctl32_slow;
+    DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, ctl32, ctl32_slow;
     // options
     double tol_scale = 1.0;
     int algo = MPCB_ALGO_AUTO;
@@ -192,7 +192,7 @@ int mpcb_destroy(mpcb_handle *h) {
     if (!h) return MPCB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->ctl32,
+    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
                       &h->lock, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j})
@@ -262,7 +262,16 @@ int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, i
     CK(h->tab64.ensure(sizeof(double4) * S)); CK(h->tab64_slow.ensure(sizeof(double4) * S));
     CK(h->vtab.ensure(sizeof(double) * S)); CK(h->vtab_slow.ensure(sizeof(double) * S));
     CK(h->beta.ensure(sizeof(double) * nb));
+    // pair table for the packed pass-1 loop; chunk boundaries (kLeafChunk, even) keep pairs intact
+    const int npairs = (S + 1) / 2;
+    std::vector<float4> l32p(2 * (size_t)npairs);
+    for (int m = 0; m < npairs; ++m) {
+        const float4 x = l32[2 * m], y = l32[std::min(2 * m + 1, S - 1)];
+        l32p[2 * m] = make_float4(x.x, y.x, x.y, y.y);
+        l32p[2 * m + 1] = make_float4(x.z, y.z, x.w, y.w);
+    }
     CK(h->leaf32.ensure(sizeof(float4) * S));
+    CK(h->leaf32p.ensure(sizeof(float4) * 2 * npairs));
     CK(h->ctl32.ensure(sizeof(float2) * S)); CK(h->ctl32_slow.ensure(sizeof(float2) * S));
     // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may die here;
     // ordering against earlier solves on the stream is preserved
@@ -272,6 +281,7 @@ int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, i
     CK(cudaMemcpyAsync(h->vtab_slow.p, vts.data(), sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->beta.p, beta, sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->leaf32.p, l32.data(), sizeof(float4) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->leaf32p.p, l32p.data(), sizeof(float4) * 2 * npairs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ctl32.p, c32.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ctl32_slow.p, c32s.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -280,6 +290,7 @@ int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, i
     g.tab64_slow = h->tab64_slow.as<double4>(); g.vtab_slow = h->vtab_slow.as<double>();
     g.beta = h->beta.as<double>();
     g.leaf32 = h->leaf32.as<float4>();
+    g.leaf32p = h->leaf32p.as<float4>();
     g.ctl32 = h->ctl32.as<float2>(); g.ctl32_slow = h->ctl32_slow.as<float2>();
     g.S = S; g.nb = nb; g.dt = delta_t; g.smax = smax; g.dphimax = dphimax;
     h->have_grid = true;
@@ -328,6 +339,7 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     unsigned *work_count = h->misc.as<unsigned>();
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
     CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
+    CK(cudaMemsetAsync(h->segmin.p, 0xFF, sizeof(double) * std::max<unsigned long long>(a.total_segs, 1), h->stream));
 
     a.sp = h->sp.as<SolveParams>();
     a.segmin = h->segmin.as<double>();

@@ -20,6 +20,13 @@
 //             tabulated displacement into the parent frame)
 #include "mpcb_types.cuh"
 
+#ifndef MPCB_UNROLL
+#define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (measured best of 1/2/4/8, profiles/r1b_variants.txt)
+#endif
+#ifndef MPCB_MINB
+#define MPCB_MINB 4     // resident CTAs per SM the pass-1 kernel is compiled for (64 regs; 5/6/8 measured slower)
+#endif
+
 #include <cfloat>
 #include <cmath>
 
@@ -46,6 +53,17 @@ __device__ __forceinline__ double warp_min(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// order-preserving map double -> uint64 (non-NaN), so that partial minima can be folded with
+// atomicMin; ~0 is the "nothing yet" value the host memsets
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? ~0ULL : 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double ordered_value(unsigned long long k) {
+    if (k == ~0ULL) return INFINITY;
+    unsigned long long b = (k >> 63) ? (k ^ 0x8000000000000000ULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
 // lexicographic (cost, index) minimum; NaN costs never win
 __device__ __forceinline__ void lex_min(double &J, long long &j, double oJ, long long oj) {
     if (oj >= 0 && (j < 0 || oJ < J || (oJ == J && oj < j))) { J = oJ; j = oj; }
@@ -61,10 +79,11 @@ struct ParentRegs {
     float e2, h2;      // 2 * wl*signed line distance of the parent, 2 * wh*(theta - phi_parent)
 };
 
-// fp32 leaf part L of the cost: J_leaf = Kbase + base_parent + L.
+// fp32 leaf part L of the cost: J_leaf = Kbase + base_parent + L,
+//   L = 1e4 (d - Dp) + line offset + heading offset.
 //   (a, b) displacement parent->leaf in the parent frame, r = a^2+b^2, g = wh * heading change
-//   FAR : d - Dp = num / (d + Dp), num = r - 2(u a + w b)   (no cancellation; needs Dp >= 4 reach)
-//   NEAR: d - Dp = |(u - a, w - b)| - Dp                     (absolute error ~ulp(reach))
+//   FAR  (|target| >= 4 reach): d - Dp = num / (d + Dp), num = r - 2(u a + w b): no cancellation
+//   NEAR: d - Dp = |(u - a, w - b)| - float(Dp); the float64 remainder of Dp sits in the base
 template <bool HEAD, bool NEAR>
 __device__ __forceinline__ float leaf_val(float a, float b, float r, float g, const ParentRegs &p) {
     float t;
@@ -82,12 +101,22 @@ __device__ __forceinline__ float leaf_val(float a, float b, float r, float g, co
     return __fmaf_rn(10000.0f, t, acc);
 }
 
-__device__ __forceinline__ void start_as_parent(const SolveParams &P, ParentRegs &pr) {
+// returns the remainder term -kWd (Dp - float(Dp)) that a NEAR parent adds to its base
+__device__ __forceinline__ double split_distance(double Dp, ParentRegs &pr) {
+    pr.D2 = (float)(Dp * Dp);
+    pr.Dp = (float)Dp;
+    return -kWd * (Dp - (double)pr.Dp);
+}
+
+// the start pose as the "parent" of every leaf (leafwalk); returns its base (remainder term only)
+__device__ __forceinline__ double start_as_parent(const SolveParams &P, ParentRegs &pr) {
     pr.u = (float)P.u0; pr.w = (float)P.w0;
     pr.u2 = (float)(-2.0 * P.u0); pr.w2 = (float)(-2.0 * P.w0);
-    pr.D2 = (float)(P.d0 * P.d0); pr.Dp = (float)P.d0;
+    const double rem = split_distance(P.d0, pr);
+    const double base = (P.flags & kFlagNear) ? rem : 0.0;
     pr.nu = (float)P.nx0; pr.nw = (float)P.ny0;
     pr.e2 = (float)(2.0 * P.e0); pr.h2 = (float)(2.0 * P.hp0);
+    return base;
 }
 
 // float64 walk of the prefix (i_0 .. i_{H-2}) of depth-(H-1) node p in the start frame, then the
@@ -111,18 +140,18 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     unmoved = (xi == 0.0 && eta == 0.0);
     double relx = P.u0 - xi, rely = P.w0 - eta;
     double u = cp * relx + sp * rely, w = cp * rely - sp * relx;
-    double D2 = u * u + w * w, Dp = sqrt(D2);
+    double Dp = sqrt(u * u + w * w);
     double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
     double nu = cp * P.nx0 + sp * P.ny0, nw = cp * P.ny0 - sp * P.nx0;
     double hp = P.hp0 - P.wh * psi;
     pr.u = (float)u; pr.w = (float)w;
     pr.u2 = (float)(-2.0 * u); pr.w2 = (float)(-2.0 * w);
-    pr.D2 = (float)D2; pr.Dp = (float)Dp;
+    const double dp_rem = split_distance(Dp, pr);
     pr.nu = (float)nu; pr.nw = (float)nw;
     pr.e2 = (float)(2.0 * ep); pr.h2 = (float)(2.0 * hp);
     near = !(Dp >= 4.0 * a.g.smax);
     // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
-    return kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
+    return kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0) + (near ? dp_rem : 0.0);
 }
 
 // float64 cost of leaf j by the reference's own formula and operation order
@@ -201,17 +230,11 @@ __device__ __forceinline__ void publish_best(const LaunchArgs &a, long long n, d
     __syncthreads();
 }
 
-__device__ __forceinline__ void publish_segmin(const LaunchArgs &a, unsigned seg, double v, double *s_J) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// pass 1: every warp folds its partial minimum into the segment's key -- no CTA barrier
+__device__ __forceinline__ void publish_segmin(const LaunchArgs &a, unsigned seg, double v) {
     v = warp_min(v);
-    if (lane == 0) s_J[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        double x = lane < kThreads / 32 ? s_J[lane] : INFINITY;
-        x = warp_min(x);
-        if (lane == 0) a.segmin[seg] = x;
-    }
-    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && v < INFINITY)
+        atomicMin(reinterpret_cast<unsigned long long *>(a.segmin) + seg, ordered_key(v));
 }
 
 // work item -> (segment, solve, tile range).  PASS 1 walks all segments, PASS 2 the work list.
@@ -236,26 +259,68 @@ __device__ __forceinline__ void decode_work(const LaunchArgs &a, unsigned long l
 
 // ------------------------------------------------------------------------------------ prefix
 // One thread per depth-(H-1) node; the S children are scored from the shared-memory table.
-template <bool HEAD, bool NEAR>
-__device__ __forceinline__ float prefix_min_loop(const float4 *__restrict__ tab, int n, const ParentRegs &pr, float best) {
-#pragma unroll 8
-    for (int c = 0; c < n; ++c) {
-        float4 t = tab[c];
-        best = fminf(best, leaf_val<HEAD, NEAR>(t.x, t.y, t.z, t.w, pr));
+// Pass-1 inner loops over the PAIR table: entry m holds leaves 2m, 2m+1 as
+//   tab[2m] = {a0, a1, b0, b1}, tab[2m+1] = {r0, r1, g0, g1}
+// so that two leaves go through one packed FFMA2/FADD2/FMUL2 each (sm_100 f32x2 pipe): the
+// FP32 part costs half the issue slots and the loop becomes XU(MUFU)-bound.
+template <bool HEAD>
+__device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
+                                                      float best) {
+    const float2 U2 = make_float2(pr.u2, pr.u2), W2 = make_float2(pr.w2, pr.w2);
+    const float2 D2 = make_float2(pr.D2, pr.D2), DP = make_float2(pr.Dp, pr.Dp);
+    const float2 NU = make_float2(pr.nu, pr.nu), NW = make_float2(pr.nw, pr.nw);
+    const float2 E2 = make_float2(pr.e2, pr.e2), NH2 = make_float2(-pr.h2, -pr.h2);
+    const float2 WD = make_float2(10000.0f, 10000.0f);
+    constexpr int kUnroll = MPCB_UNROLL;
+#pragma unroll kUnroll
+    for (int m = 0; m < npairs; ++m) {
+        const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
+        const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
+        const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
+        const float2 num = __ffma2_rn(U2, A, __ffma2_rn(W2, B, R));
+        const float2 dd = __fadd2_rn(D2, num);
+        const float2 den = __fadd2_rn(make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)), DP);
+        // both reciprocals of the pair from ONE MUFU.RCP (Montgomery): 1/y0 = y1/(y0 y1), 1/y1 = y0/(y0 y1)
+        const float rp = rcp_approx(den.x * den.y);
+        const float2 t = __fmul2_rn(num, __fmul2_rn(make_float2(rp, rp), make_float2(den.y, den.x)));
+        const float2 q = __ffma2_rn(NU, A, __fmul2_rn(NW, B));
+        float2 acc = __fmul2_rn(q, __fadd2_rn(E2, q));
+        if (HEAD) acc = __ffma2_rn(G, __fadd2_rn(G, NH2), acc);
+        const float2 L = __ffma2_rn(WD, t, acc);
+        best = fminf(best, fminf(L.x, L.y));
+    }
+    return best;
+}
+
+// scalar flavour on the same pair table: NEAR regime, or a node sitting exactly on the line origin
+template <bool HEAD>
+__device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
+                                                        bool near, bool special, float Lspecial, float best) {
+    for (int m = 0; m < npairs; ++m) {
+        const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
+        float L0 = near ? leaf_val<HEAD, true>(t0.x, t0.z, t1.x, t1.z, pr) : leaf_val<HEAD, false>(t0.x, t0.z, t1.x, t1.z, pr);
+        float L1 = near ? leaf_val<HEAD, true>(t0.y, t0.w, t1.y, t1.w, pr) : leaf_val<HEAD, false>(t0.y, t0.w, t1.y, t1.w, pr);
+        if (special && t1.x == 0.f) L0 = Lspecial;
+        if (special && t1.y == 0.f) L1 = Lspecial;
+        best = fminf(best, fminf(L0, L1));
     }
     return best;
 }
 
 template <int PASS, bool HEAD>
-__global__ void __launch_bounds__(kThreads) prefix_kernel(const LaunchArgs a) {
+__global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
     __shared__ double s_J[kThreads / 32];
     __shared__ long long s_j[kThreads / 32];
     const int tid = threadIdx.x;
     const int S = a.g.S;
     const bool single = S <= kLeafChunk;
+    // pass 1 stages the PAIR table (2 float4 per 2 leaves), pass 2 the plain per-leaf table;
+    // either way a chunk of kLeafChunk leaves is kLeafChunk float4
+    const float4 *__restrict__ gtab = PASS == 1 ? a.g.leaf32p : a.g.leaf32;
+    auto chunk_f4 = [&](int cn) { return PASS == 1 ? 2 * ((cn + 1) >> 1) : cn; };
     if (single) {
-        for (int i = tid; i < S; i += kThreads) s_leaf[i] = __ldg(a.g.leaf32 + i);
+        for (int i = tid; i < chunk_f4(S); i += kThreads) s_leaf[i] = __ldg(gtab + i);
         __syncthreads();
     }
     const unsigned long long nwork =
@@ -284,22 +349,21 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const LaunchArgs a) {
                 const int cn = min(kLeafChunk, S - c0);
                 if (!single) {
                     __syncthreads();
-                    for (int i = tid; i < cn; i += kThreads) s_leaf[i] = __ldg(a.g.leaf32 + c0 + i);
+                    for (int i = tid; i < chunk_f4(cn); i += kThreads) s_leaf[i] = __ldg(gtab + c0 + i);
                     __syncthreads();
                 }
                 if (!active) continue;
-                if (PASS == 1 && !special) {
-                    best = near ? prefix_min_loop<HEAD, true>(s_leaf, cn, pr, best)
-                                : prefix_min_loop<HEAD, false>(s_leaf, cn, pr, best);
+                if (PASS == 1) {
+                    const int npairs = (cn + 1) >> 1;
+                    best = (near || special) ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr, near, special, Lspecial, best)
+                                             : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr, best);
                 } else {
-                    // refinement pass, or a node sitting exactly on the line origin (rare)
                     for (int c = 0; c < cn; ++c) {
                         float4 t = s_leaf[c];
                         float L = near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
                                        : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
                         if (special && t.z == 0.f) L = Lspecial;
-                        if (PASS == 1) best = fminf(best, L);
-                        else if (L <= thr)
+                        if (L <= thr)
                             take_candidate(a, P, (long long)(p * (unsigned long long)S + c0 + c),
                                            base + (double)L, bJ, bj);
                     }
@@ -307,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) prefix_kernel(const LaunchArgs a) {
             }
             if (PASS == 1 && active) segbest = fmin(segbest, base + (double)best);
         }
-        if (PASS == 1) publish_segmin(a, seg, segbest, s_J);
+        if (PASS == 1) publish_segmin(a, seg, segbest);
         else publish_best(a, n, bJ, bj, s_J, s_j);
     }
 }
@@ -353,9 +417,9 @@ __global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) 
         decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
         const SolveParams &P = a.sp[n];
         ParentRegs pr;
-        start_as_parent(P, pr);
+        const double base = start_as_parent(P, pr);
         const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
-        const float thr = PASS == 2 ? __double2float_ru(a.tau[n]) : 0.f;
+        const float thr = PASS == 2 ? __double2float_ru(a.tau[n] - base) : 0.f;
         if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
         float best = INFINITY;
         double bJ = INFINITY; long long bj = -1;
@@ -365,9 +429,9 @@ __global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) 
             float xi, eta, psi;
             const float L = leafwalk_eval<HEAD>(a, P, pr, ctl, j, xi, eta, psi);
             if (PASS == 1) best = fminf(best, L);
-            else if (L <= thr) take_candidate(a, P, (long long)j, (double)L, bJ, bj);
+            else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
         }
-        if (PASS == 1) publish_segmin(a, seg, (double)best, s_J);
+        if (PASS == 1) publish_segmin(a, seg, base + (double)best);
         else publish_best(a, n, bJ, bj, s_J, s_j);
     }
 }
@@ -379,7 +443,7 @@ template <bool HEAD>
 __global__ void __launch_bounds__(kThreads) leafwalk_dump_kernel(const LaunchArgs a, double *jrel) {
     const SolveParams &P = a.sp[0];
     ParentRegs pr;
-    start_as_parent(P, pr);
+    const double base = start_as_parent(P, pr);
     const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
     const float c0 = (float)cos(P.phi0), s0 = (float)sin(P.phi0);
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < a.dump_count;
@@ -388,7 +452,7 @@ __global__ void __launch_bounds__(kThreads) leafwalk_dump_kernel(const LaunchArg
         const float L = leafwalk_eval<HEAD>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi);
         a.dump[i] = make_float4((float)P.xs + (c0 * xi - s0 * eta), (float)P.ys + (s0 * xi + c0 * eta),
                                 (float)P.phi0 + psi, L);
-        jrel[i] = (double)L;
+        jrel[i] = base + (double)L;
     }
 }
 
@@ -471,9 +535,9 @@ __global__ void __launch_bounds__(kThreads) reduce_compact_kernel(const LaunchAr
     __shared__ double s_tau;
     const unsigned sps = (unsigned)a.segs_per_solve;
     for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
-        const double *sm = a.segmin + (unsigned long long)n * sps;
+        const unsigned long long *sm = reinterpret_cast<const unsigned long long *>(a.segmin) + (unsigned long long)n * sps;
         double v = INFINITY;
-        for (unsigned i = threadIdx.x; i < sps; i += kThreads) v = fmin(v, sm[i]);
+        for (unsigned i = threadIdx.x; i < sps; i += kThreads) v = fmin(v, ordered_value(sm[i]));
         v = warp_min(v);
         if ((threadIdx.x & 31) == 0) s_J[threadIdx.x >> 5] = v;
         __syncthreads();
@@ -490,7 +554,7 @@ __global__ void __launch_bounds__(kThreads) reduce_compact_kernel(const LaunchAr
         const double t = s_tau;
         if (t < INFINITY)
             for (unsigned i = threadIdx.x; i < sps; i += kThreads)
-                if (sm[i] <= t) worklist[atomicAdd(work_count, 1u)] = (unsigned)(n * sps + i);
+                if (ordered_value(sm[i]) <= t) worklist[atomicAdd(work_count, 1u)] = (unsigned)(n * sps + i);
         __syncthreads();
     }
 }

@@ -40,6 +40,7 @@ struct GridTables {
     const double  *beta;        // beta[nb]
     // float32, for the inner loops
     const float4 *leaf32;       // {a_c = s_c cos dphi_c, b_c = s_c sin dphi_c, r_c = s_c^2, g_c = sqrt(10) dphi_c}
+    const float4 *leaf32p;      // pair table: [2m] = {a_2m, a_2m+1, b_2m, b_2m+1}, [2m+1] = {r.., r.., g.., g..}; odd S pads by repeating the last leaf
     const float2 *ctl32;        // {dphi_c, s_c}
     const float2 *ctl32_slow;
     int S, nb;
