@@ -193,6 +193,37 @@ class Solver:
         return xy, cs
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id (rank 0 creates it, the caller distributes it)."""
+    buf = C.create_string_buffer(128)
+    rc = load().mpcb_nccl_unique_id(buf)
+    if rc != 0:
+        raise MpcbError(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+class NcclComm:
+    """Native NCCL communicator bound to a Solver's device (mpcb_nccl_comm_create)."""
+
+    def __init__(self, solver: "Solver", nranks: int, rank: int, unique_id: bytes):
+        self.solver = solver
+        self.comm = C.c_void_p()
+        rc = solver.lib.mpcb_nccl_comm_create(solver.h, nranks, rank, C.c_char_p(unique_id), C.byref(self.comm))
+        if rc != 0:
+            raise MpcbError(rc, "ncclCommInitRank failed")
+
+    def allreduce_min(self, cost_ptr: int, index_ptr: int):
+        """Lexicographic (cost, index) min over ranks, in place on 1-element device buffers."""
+        rc = self.solver.lib.mpcb_allreduce_min(self.solver.h, self.comm, C.c_void_p(cost_ptr), C.c_void_p(index_ptr))
+        if rc != 0:
+            raise MpcbError(rc, "mpcb_allreduce_min failed")
+
+    def close(self):
+        if self.comm:
+            self.solver.lib.mpcb_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+
 _default = {}
 
 

@@ -13,10 +13,19 @@ class OracleBackend:
 
     def set_grid(self, vector_v, vector_beta, L, delta_t, v_min=0.0):
         self.grid = (list(vector_v), list(vector_beta), L, delta_t, v_min)
+        self.S = len(self.grid[0]) * len(self.grid[1])
 
     def solve(self, mode, cost, H, state, target, origin, threshold=None, flags=None, i0_range=None):
         V, B, L, dt, v_min = self.grid
         self.calls += 1
+        st = np.asarray(state, float)
+        if st.ndim == 2:      # batch: loop
+            tg = np.asarray(target, float).reshape(-1, 2); og = np.asarray(origin, float).reshape(-1, 2)
+            n = st.shape[0]
+            rs = [self.solve(mode, cost, H, st[i], tg[i if tg.shape[0] == n else 0], og[i if og.shape[0] == n else 0],
+                             None if threshold is None else np.broadcast_to(threshold, (n,))[i],
+                             None if flags is None else np.broadcast_to(flags, (n,))[i], i0_range) for i in range(n)]
+            return {k: np.concatenate([r[k] for r in rs], axis=0) for k in rs[0]}
         thr = np.inf if threshold is None else float(threshold)
         ck = C.COST_MM if cost == 0 else C.COST_TREE
         if mode == 1:
