@@ -36,6 +36,26 @@ class Stats(C.Structure):
                 ("algo", C.c_int32), ("kernel_launches", C.c_int32)]
 
 
+class LoopParams(C.Structure):
+    """mpcb_loop_params (include/mpcb200.h)."""
+    _fields_ = [("L", C.c_double), ("delta_t", C.c_double), ("delta_v", C.c_double), ("delta_beta", C.c_double),
+                ("v_max", C.c_double), ("v_min", C.c_double), ("beta_limit", C.c_double), ("half_v", C.c_double),
+                ("half_beta", C.c_double), ("eps", C.c_double), ("n_v", C.c_int32), ("n_beta", C.c_int32),
+                ("cost_kind", C.c_int32), ("H", C.c_int32), ("max_ticks", C.c_int32), ("reserved", C.c_int32)]
+
+    @classmethod
+    def from_config(cls, cfg, cost_kind=COST_TREE, H=3, max_ticks=512):
+        """Window constants computed exactly as math_model_tree.py:239-256 computes them."""
+        half_v = (cfg.v_acc_max * cfg.delta_t) / cfg.delta_v
+        half_b = (math.degrees(cfg.beta_acc_max) * cfg.delta_t) / math.degrees(cfg.delta_beta)
+        return cls(L=cfg.L, delta_t=cfg.delta_t, delta_v=cfg.delta_v, delta_beta=cfg.delta_beta, v_max=cfg.v_max,
+                   v_min=cfg.v_min, beta_limit=cfg.beta_max + math.radians(cfg.eps_beta), half_v=half_v,
+                   half_beta=half_b, eps=cfg.eps, n_v=1 + 2 * int(half_v), n_beta=1 + 2 * int(half_b),
+                   cost_kind=cost_kind, H=H, max_ticks=max_ticks, reserved=0)
+
+
+LOOP_ON_TARGET, LOOP_STALLED, LOOP_MAX_TICKS, LOOP_NO_LEAF = 0, 1, 2, 3
+
 _lib = None
 _dp, _i64p, _u8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
 
@@ -71,6 +91,9 @@ def load():
     lib.mpcb_dump_leaves_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_uint8,
                                           C.c_int64, C.c_int64, _fp, _dp]
     lib.mpcb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    loop = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mpcb_held_closed_loop_host.argtypes = loop
+    lib.mpcb_held_closed_loop_device.argtypes = loop
     lib.mpcb_allreduce_min.argtypes = [vp, vp, vp, vp]
     lib.mpcb_nccl_unique_id.argtypes = [vp]
     lib.mpcb_nccl_comm_create.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
@@ -177,6 +200,22 @@ class Solver:
         self._ck(self.lib.mpcb_solve_batch_device(self.h, mode, cost, H, int(N), vp(state), vp(target), vp(origin),
                                                   vp(threshold), vp(flags), lo, hi, vp(out_cost), vp(out_index),
                                                   vp(out_traj), vp(out_ctl)))
+
+    def held_closed_loop(self, params: "LoopParams", init, target, origin, first_threshold=None, slow_steps=None):
+        """Whole closed loops of the online controller for a batch of robots on the device
+        (mpcb_held_closed_loop_host). Returns dict(log[N,max_ticks,5], ticks[N], status[N])."""
+        ini = _arr(init, np.float64, (-1, 5))
+        N = ini.shape[0]
+        tg = _arr(np.broadcast_to(np.asarray(target, np.float64).reshape(-1, 2), (N, 2)), np.float64)
+        og = _arr(np.broadcast_to(np.asarray(origin, np.float64).reshape(-1, 2), (N, 2)), np.float64)
+        thr = None if first_threshold is None else _arr(np.broadcast_to(np.asarray(first_threshold, np.float64), (N,)), np.float64)
+        sl = None if slow_steps is None else _arr(np.broadcast_to(np.asarray(slow_steps, np.int32), (N,)), np.int32)
+        log = np.full((N, params.max_ticks, 5), np.nan)
+        ticks = np.empty(N, np.int32)
+        status = np.empty(N, np.int32)
+        self._ck(self.lib.mpcb_held_closed_loop_host(self.h, C.byref(params), N, _ptr(ini), _ptr(tg), _ptr(og), _ptr(thr),
+                                                     _ptr(sl), _ptr(log), _ptr(ticks), _ptr(status)))
+        return dict(log=log, ticks=ticks, status=status)
 
     def dump_leaves(self, mode, cost, H, state, target, origin, flags=0, algo=ALGO_LEAFWALK, leaf_begin=0, count=None):
         st = _arr(state, np.float64).ravel()[:3].copy()

@@ -21,6 +21,7 @@ cudaError_t launch_pass(cudaStream_t, const LaunchArgs &, int pass, bool prefix,
 cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, unsigned *, unsigned *, int sms);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
+cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
 }  // namespace mpcb
 
 using namespace mpcb;
@@ -72,6 +73,7 @@ struct mpcb_handle_s {
     // scratch
     DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock;
     DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
+    DevBuf loop_log, loop_ticks, loop_status;
     mpcb_stats stats{};
     unsigned long long last_counters_pending = 0;
 };
@@ -195,7 +197,8 @@ int mpcb_destroy(mpcb_handle *h) {
     for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
                       &h->lock, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
-                      &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j})
+                      &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
+                      &h->loop_status})
         b->release();
     cudaStreamDestroy(h->stream);
     delete h;
@@ -482,6 +485,72 @@ int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int al
         if (xy) { xy[2 * i] = rec[i].x; xy[2 * i + 1] = rec[i].y; }
         if (cost) cost[i] = P.Kbase + jr[i];
     }
+    return MPCB_OK;
+}
+
+int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
+                                 const double *target, const double *origin, const double *first_threshold,
+                                 const int32_t *slow_steps, double *out_log, int32_t *out_ticks, int32_t *out_status) {
+    if (!h || !p) return MPCB_ERR_INVALID;
+    if (N < 0 || N >= (1LL << 31)) return fail(h, MPCB_ERR_INVALID, "N out of range");
+    if (N == 0) return MPCB_OK;
+    if (!init || !target || !origin || !out_log || !out_ticks || !out_status)
+        return fail(h, MPCB_ERR_INVALID, "closed loop: null pointer");
+    if (p->H < 1 || p->H > MPCB_MAX_H || p->max_ticks < 1 || p->n_v < 1 || p->n_beta < 1 || p->n_v > 128 || p->n_beta > 128)
+        return fail(h, MPCB_ERR_INVALID, "closed loop: bad parameters (H=%d, max_ticks=%d, n_v=%d, n_beta=%d)", p->H,
+                    p->max_ticks, p->n_v, p->n_beta);
+    CK(cudaSetDevice(h->device));
+    LoopArgs a;
+    a.p = *p; a.N = N;
+    a.init = init; a.target = target; a.origin = origin; a.first_threshold = first_threshold;
+    a.slow_steps = slow_steps; a.out_log = out_log; a.out_ticks = out_ticks; a.out_status = out_status;
+    CK(launch_held_loop(h->stream, a, h->sms));
+    h->stats = mpcb_stats{};
+    h->stats.kernel_launches = 1;
+    h->stats.algo = MPCB_ALGO_LEAFWALK;
+    return MPCB_OK;
+}
+
+int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
+                               const double *target, const double *origin, const double *first_threshold,
+                               const int32_t *slow_steps, double *out_log, int32_t *out_ticks, int32_t *out_status) {
+    if (!h || !p) return MPCB_ERR_INVALID;
+    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
+    if (!init || !target || !origin || !out_log || !out_ticks || !out_status)
+        return fail(h, MPCB_ERR_INVALID, "closed loop: null pointer");
+    if (p->max_ticks < 1) return fail(h, MPCB_ERR_INVALID, "closed loop: max_ticks < 1");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t nlog = (size_t)N * p->max_ticks * 5;
+    CK(h->in_state.ensure(sizeof(double) * 5 * N));
+    CK(h->in_target.ensure(sizeof(double) * 2 * N));
+    CK(h->in_origin.ensure(sizeof(double) * 2 * N));
+    CK(h->loop_log.ensure(sizeof(double) * nlog));
+    CK(h->loop_ticks.ensure(sizeof(int) * N));
+    CK(h->loop_status.ensure(sizeof(int) * N));
+    CK(cudaMemcpyAsync(h->in_state.p, init, sizeof(double) * 5 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_target.p, target, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_origin.p, origin, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    const double *d_thr = nullptr;
+    const int *d_slow = nullptr;
+    if (first_threshold) {
+        CK(h->in_thr.ensure(sizeof(double) * N));
+        CK(cudaMemcpyAsync(h->in_thr.p, first_threshold, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        d_thr = h->in_thr.as<double>();
+    }
+    if (slow_steps) {
+        CK(h->in_flags.ensure(sizeof(int) * N));
+        CK(cudaMemcpyAsync(h->in_flags.p, slow_steps, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+        d_slow = h->in_flags.as<int>();
+    }
+    int rc = mpcb_held_closed_loop_device(h, p, N, h->in_state.as<double>(), h->in_target.as<double>(),
+                                          h->in_origin.as<double>(), d_thr, d_slow, h->loop_log.as<double>(),
+                                          h->loop_ticks.as<int>(), h->loop_status.as<int>());
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_log, h->loop_log.p, sizeof(double) * nlog, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_ticks, h->loop_ticks.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_status, h->loop_status.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return MPCB_OK;
 }
 

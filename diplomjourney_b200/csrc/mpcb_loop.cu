@@ -1,0 +1,203 @@
+// mpcb_loop.cu -- device-resident closed loop of the online (HELD) controller: SURVEY 8f rows f1+f2.
+//
+// One CTA per robot runs the whole tick loop of math_mpc(..., isActual=False)
+// (math_model_tree.py:542-579) without returning to the host:
+//   per tick  windows   vector_of_velocities / vector_of_beta_angles      math_model_tree.py:239-256
+//             solve     HELD predictive_control, slow-down override        math_model_tree.py:308-361
+//             apply     finishing heuristic m, result pose, threshold reset math_model_tree.py:388-429
+//             stop      is_on_target, repeated-position ("Recursive error") math_model_tree.py:48-52,559-563
+// The scripted operator events of the reference's demo run (ticks 60/90/110) are host logic and
+// are not part of this loop.
+//
+// A HELD tick is tiny (S <= 451 candidates x H steps), so the loop is latency-bound, not
+// throughput-bound: everything is evaluated directly in float64 with the reference's formula and
+// operation order -- no fp32 stage, no refinement -- and the batch dimension (robots) fills the GPU.
+#include "mpcb_types.cuh"
+
+#include <cmath>
+
+namespace mpcb {
+
+constexpr int kLoopThreads = 256;
+constexpr int kMaxWin = 128;     // max candidates per axis of the acceleration window
+
+__device__ __forceinline__ void lex_min_d(double &J, int &j, double oJ, int oj) {
+    if (oj >= 0 && (j < 0 || oJ < J || (oJ == J && oj < j))) { J = oJ; j = oj; }
+}
+
+struct LoopCost {
+    double xt, yt, ox, oy, A, B, C, norm, theta;
+    int kind;
+    __device__ double operator()(double x, double y, double phi) const {
+        double dx = xt - x, dy = yt - y;
+        double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        double dl;
+        if (x == ox && y == oy) dl = 1000.0;
+        else dl = fabs(__dadd_rn(__dadd_rn(__dmul_rn(A, x), -__dmul_rn(B, y)), C)) / norm;
+        double dl2 = __dmul_rn(dl, dl);
+        if (kind == 0) {
+            double ang = theta - phi;
+            return __dadd_rn(__dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10.0, __dmul_rn(ang, ang))),
+                             __dmul_rn(100.0, dl2));
+        }
+        return __dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10000.0, dl2));
+    }
+};
+
+// H steps of control (v, tan beta) from (x, y, phi); optionally records the poses
+__device__ __forceinline__ void loop_walk(const mpcb_loop_params &p, double v, double tb, double &x, double &y,
+                                          double &phi, double *poses) {
+    const double dphi = __dmul_rn(__dmul_rn(__ddiv_rn(v, p.L), tb), p.delta_t);
+    for (int k = 0; k < p.H; ++k) {
+        phi = __dadd_rn(phi, dphi);
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        x = __dadd_rn(x, __dmul_rn(__dmul_rn(v, cs), p.delta_t));
+        y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, sn), p.delta_t));
+        if (poses) { poses[3 * k] = x; poses[3 * k + 1] = y; poses[3 * k + 2] = phi; }
+    }
+}
+
+__global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs a) {
+    __shared__ double s_V[kMaxWin], s_B[kMaxWin], s_tanB[kMaxWin];
+    __shared__ double s_J[kLoopThreads / 32];
+    __shared__ int s_j[kLoopThreads / 32];
+    __shared__ double s_state[5];      // x, y, phi, v, beta fed to the next tick
+    __shared__ int s_ctl[4];           // nV, nB, slow flag, stop flag
+    __shared__ double s_vslow;
+    const mpcb_loop_params &p = a.p;
+    const int tid = threadIdx.x;
+
+    for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
+        LoopCost cost;
+        cost.xt = a.target[2 * n]; cost.yt = a.target[2 * n + 1];
+        cost.ox = a.origin[2 * n]; cost.oy = a.origin[2 * n + 1];
+        cost.A = cost.yt - cost.oy; cost.B = cost.xt - cost.ox;
+        cost.C = cost.xt * cost.oy - cost.yt * cost.ox;
+        cost.norm = sqrt(cost.A * cost.A + cost.B * cost.B);
+        cost.theta = atan(cost.xt / cost.yt);
+        cost.kind = p.cost_kind;
+        // thread-0 state of the loop (math_mpc locals and the module globals it touches)
+        double thr = a.first_threshold ? a.first_threshold[n] : INFINITY;
+        int slow_steps = a.slow_steps ? a.slow_steps[n] : 0;
+        int m = 0, ticks = 0, status = 2;
+        bool recursive = false, have_traj = false;
+        double opt[3 * MPCB_MAX_H], res_v = 0.0, res_beta = 0.0;
+        double xprev = 0.0, yprev = 0.0;
+        if (tid == 0) {
+            for (int k = 0; k < 5; ++k) s_state[k] = a.init[5 * n + k];
+            xprev = s_state[0]; yprev = s_state[1];
+        }
+        __syncthreads();
+
+        for (;;) {
+            // ---- stop test + acceleration windows (thread 0, serial: <= n_v + n_beta candidates)
+            if (tid == 0) {
+                const double x = s_state[0], y = s_state[1];
+                const double dx = cost.xt - x, dy = cost.yt - y;
+                int stop = 0;
+                if (dx * dx + dy * dy <= p.eps) { stop = 1; status = 0; }
+                else if (ticks >= p.max_ticks) { stop = 1; status = 2; }
+                int nV = 0, nB = 0;
+                if (!stop) {
+                    const double v = s_state[3], beta = s_state[4];
+                    double vmin = INFINITY;
+                    for (int i = 0; i < p.n_v && nV < kMaxWin; ++i) {
+                        const double pv = __dadd_rn(v, __dmul_rn(p.delta_v, (double)i - p.half_v));
+                        if (!(pv < 0.0) && pv < p.v_max) { s_V[nV++] = pv; vmin = fmin(vmin, pv); }
+                    }
+                    for (int i = 0; i < p.n_beta && nB < kMaxWin; ++i) {
+                        const double pa = __dadd_rn(beta, __dmul_rn(p.delta_beta, (double)i - p.half_beta));
+                        if (fabs(pa) <= p.beta_limit) s_B[nB++] = pa;
+                    }
+                    s_vslow = vmin > p.v_min ? vmin : p.v_min;
+                }
+                s_ctl[0] = nV; s_ctl[1] = nB; s_ctl[2] = slow_steps > 0; s_ctl[3] = stop;
+            }
+            __syncthreads();
+            if (s_ctl[3]) break;
+            const int nV = s_ctl[0], nB = s_ctl[1];
+            const bool slow = s_ctl[2] != 0;
+            for (int i = tid; i < nB; i += kLoopThreads) s_tanB[i] = tan(s_B[i]);
+            __syncthreads();
+
+            // ---- HELD solve: candidate c = iv*nB + ib holds (v, beta) for all H steps
+            const int S = nV * nB;
+            const double x0 = s_state[0], y0 = s_state[1], phi0 = s_state[2];
+            double bJ = INFINITY; int bj = -1;
+            for (int c = tid; c < S; c += kLoopThreads) {
+                const int iv = c / nB, ib = c - iv * nB;
+                const double v = slow ? s_vslow : s_V[iv];
+                double x = x0, y = y0, phi = phi0;
+                loop_walk(p, v, s_tanB[ib], x, y, phi, nullptr);
+                const double J = cost(x, y, phi);
+                lex_min_d(bJ, bj, J, c);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oJ = __shfl_xor_sync(0xffffffffu, bJ, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                lex_min_d(bJ, bj, oJ, oj);
+            }
+            if ((tid & 31) == 0) { s_J[tid >> 5] = bJ; s_j[tid >> 5] = bj; }
+            __syncthreads();
+
+            // ---- apply (thread 0)
+            if (tid == 0) {
+                for (int i = 1; i < kLoopThreads / 32; ++i) lex_min_d(bJ, bj, s_J[i], s_j[i]);
+                if (bj >= 0 && bJ < thr) {                  // strict '<' (math_model_tree.py:351)
+                    const int iv = bj / nB, ib = bj - iv * nB;
+                    res_v = slow ? s_vslow : s_V[iv];
+                    res_beta = s_B[ib];
+                    double x = x0, y = y0, phi = phi0;
+                    loop_walk(p, res_v, s_tanB[ib], x, y, phi, opt);
+                    have_traj = true;
+                }
+                slow_steps -= 1;
+                int stop = 0;
+                if (!have_traj) { stop = 1; status = 3; }   // reference: IndexError on the [[[0]]] placeholder
+                else {
+                    // finishing heuristic (math_model_tree.py:392-414)
+                    int pick = 0;
+                    const int last = 3 * (p.H - 1);
+                    if (m == 2) pick = 2;
+                    else if (m == 1) { pick = 1; m += 1; }
+                    else {
+                        const double ex = cost.xt - opt[last], ey = cost.yt - opt[last + 1];
+                        if (ex * ex + ey * ey <= p.eps) m += 1;
+                    }
+                    if (pick > p.H - 1) pick = p.H - 1;
+                    const double rx = opt[3 * pick], ry = opt[3 * pick + 1], rphi = opt[3 * pick + 2];
+                    thr = 9223372036854775807.0;            // sys.maxsize (math_model_tree.py:428)
+                    double *log = a.out_log + ((size_t)n * p.max_ticks + ticks) * 5;
+                    log[0] = rx; log[1] = ry; log[2] = rphi; log[3] = res_v; log[4] = res_beta;
+                    s_state[0] = rx; s_state[1] = ry; s_state[2] = rphi; s_state[3] = res_v; s_state[4] = res_beta;
+                    ticks += 1;
+                    if (recursive) { stop = 1; status = 1; }        // "Recursive error." (math_model_tree.py:559-561)
+                    else if (rx == xprev && ry == yprev) recursive = true;
+                    xprev = rx; yprev = ry;
+                }
+                s_ctl[3] = stop;
+            }
+            __syncthreads();
+            if (s_ctl[3]) break;
+        }
+        if (tid == 0) {
+            a.out_ticks[n] = ticks;
+            a.out_status[n] = status;
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_held_loop(cudaStream_t st, const LoopArgs &a, int sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, held_loop_kernel, kLoopThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.N) grid = a.N;
+    held_loop_kernel<<<(unsigned)grid, kLoopThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mpcb

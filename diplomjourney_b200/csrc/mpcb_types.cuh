@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/mpcb200.h"
+
 namespace mpcb {
 
 constexpr int kThreads = 256;      // threads per CTA; one "unit" (leaf or depth-(H-1) node) per thread
@@ -90,6 +92,16 @@ struct LaunchArgs {
     // dump
     float4 *dump;                          // {x, y, phi, J_rel} per leaf
     unsigned long long dump_begin, dump_count;
+};
+
+// device-resident closed loop (mpcb_loop.cu)
+struct LoopArgs {
+    mpcb_loop_params p;
+    long long N;
+    const double *init, *target, *origin, *first_threshold;
+    const int *slow_steps;
+    double *out_log;
+    int *out_ticks, *out_status;
 };
 
 }  // namespace mpcb

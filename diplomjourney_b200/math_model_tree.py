@@ -298,10 +298,13 @@ def add_plot_polygon(coordinates_of_vertexes):
 
 
 need_scatter = False
+scripted_events = True      # the demo run's operator events at ticks 1/60/90/110; set False for a plain run
 
 
 def _scripted_events(tick, px, py, pphi, pv, isActual):
     """Operator events of the demo run (math_model_tree.py:564-569,617-624)."""
+    if not scripted_events:
+        return
     if isActual and tick == 1:
         new_target(px, py, pphi, 2, 3, pv)
     if tick == 60:
@@ -351,6 +354,34 @@ def math_mpc(initial_coordinates, target_coordinates, isActual):
             result_y_velocity.append(pv * np.sin(pphi))
             result_y_acceleration.append(((pv - previous_v) / delta_t) * np.sin(pphi))
     t = 0
+
+
+def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origin=None, cost_kind=None):
+    """EXTENSION (not in the reference): the closed loop of ``math_mpc(..., isActual=False)`` for a
+    whole batch of robots, executed on the GPU without returning to the host between ticks
+    (one CTA per robot; no scripted operator events).  ``initial_coordinates`` [N][5] =
+    x, y, phi, v, beta; ``target_coordinates`` [N][2].  The tracked line starts at the module's
+    x_0, y_0 unless ``origin`` [N][2] is given.  Returns dict(log[N][max_ticks][5], ticks[N], status[N])."""
+    from . import config as _cfg
+    params = _native.LoopParams.from_config(_cfg, _native.COST_TREE if cost_kind is None else cost_kind,
+                                            prediction_horizon, max_ticks)
+    ini = np.asarray(initial_coordinates, dtype=np.float64).reshape(-1, 5)
+    org = np.array([[x_0, y_0]], dtype=np.float64) if origin is None else np.asarray(origin, np.float64).reshape(-1, 2)
+    tgt = np.asarray(target_coordinates, dtype=np.float64).reshape(-1, 2)
+    n = ini.shape[0]
+    org = np.broadcast_to(org, (n, 2))
+    tgt = np.broadcast_to(tgt, (n, 2))
+    # optimal_criterion before the first tick = control_criterion of the line origin (math_model_tree.py:676)
+    saved = (x_t, y_t, x_0, y_0)
+    g = globals()
+    first = np.empty(n)
+    try:
+        for i in range(n):
+            g.update(x_t=tgt[i, 0], y_t=tgt[i, 1], x_0=org[i, 0], y_0=org[i, 1])
+            first[i] = control_criterion([org[i, 0], org[i, 1], phi_0])
+    finally:
+        g.update(x_t=saved[0], y_t=saved[1], x_0=saved[2], y_0=saved[3])
+    return _solver().held_closed_loop(params, ini, tgt, org, first_threshold=first)
 
 
 def reset_state():

@@ -137,6 +137,47 @@ typedef struct {
 } mpcb_stats;
 MPCB_API int mpcb_get_stats(mpcb_handle *h, mpcb_stats *out);
 
+/* Device-resident closed loop of the online (HELD) controller for a batch of robots: the tick loop
+ * of math_mpc(initial, target, isActual=False) (math_model_tree.py:515-579, without the scripted
+ * operator events of the demo run) -- windows vector_of_velocities / vector_of_beta_angles
+ * (math_model_tree.py:239-256), HELD solve with the slow-down override (:308-361), finishing
+ * heuristic and threshold reset (:388-429), is_on_target and repeated-position stop (:542,559-563) --
+ * executed entirely on the GPU, one CTA per robot, float64 throughout.
+ * The host computes the window constants exactly as the reference does and passes them in. */
+typedef struct {
+    double L, delta_t;
+    double delta_v, delta_beta;
+    double v_max, v_min;
+    double beta_limit;      /* beta_max + radians(eps_beta)                   (math_model_tree.py:254) */
+    double half_v;          /* (v_acc_max*delta_t)/delta_v                    (math_model_tree.py:241-243) */
+    double half_beta;       /* (degrees(beta_acc_max)*delta_t)/degrees(delta_beta) (:251-253) */
+    double eps;             /* is_on_target tolerance on the squared distance (:49) */
+    int32_t n_v, n_beta;    /* 1 + 2*int(half_v), 1 + 2*int(half_beta) */
+    int32_t cost_kind, H;   /* MPCB_COST_*, horizon (3 in the reference) */
+    int32_t max_ticks, reserved;
+} mpcb_loop_params;
+
+/* per-robot stop reason */
+#define MPCB_LOOP_ON_TARGET 0
+#define MPCB_LOOP_STALLED 1    /* the reference's "Recursive error." */
+#define MPCB_LOOP_MAX_TICKS 2
+#define MPCB_LOOP_NO_LEAF 3    /* first tick found no acceptable leaf (the reference raises IndexError) */
+
+/*   init[N][5]            x, y, phi, v, beta     target[N][2], origin[N][2] as for mpcb_solve_batch
+ *   first_threshold[N]    optimal_criterion before the first tick (control_criterion of the line
+ *                         origin in the reference, math_model_tree.py:676); NULL = +inf
+ *   slow_steps[N]         steps_for_slowing at entry; NULL = 0
+ *   out_log[N][max_ticks][5]  the 5-list returned by every tick (x, y, phi, v, beta)
+ *   out_ticks[N], out_status[N] */
+MPCB_API int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N,
+                               const double *init, const double *target, const double *origin,
+                               const double *first_threshold, const int32_t *slow_steps,
+                               double *out_log, int32_t *out_ticks, int32_t *out_status);
+MPCB_API int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params *p, int64_t N,
+                                 const double *init, const double *target, const double *origin,
+                                 const double *first_threshold, const int32_t *slow_steps,
+                                 double *out_log, int32_t *out_ticks, int32_t *out_status);
+
 /* Cross-rank reconciliation of a split tree: lexicographic (cost, index) minimum over the
  * ranks of an NCCL communicator (two 8-byte all-reduce-min rounds, exact for float64 costs
  * and 63-bit indices).  comm is an ncclComm_t; cost/index are device pointers (1 element). */

@@ -99,6 +99,24 @@ def gen_held_closed_loop():
     return dict(meta=_meta(), call="math_mpc([0,0,0,0,0],[2,3],False)", cost="tree", H=3, log=out)
 
 
+def gen_held_short_loops():
+    """Event-free closed loops: targets close enough that math_mpc finishes before its first
+    scripted operator event at tick 60 (math_model_tree.py:564)."""
+    cases = []
+    for init, tgt in (([0, 0, 0, 0, 0], [1.0, 0.8]), ([0, 0, 1.0, 0, 0], [0.3, 1.1]),
+                      ([0.2, -0.1, -0.7, 0.3, 0.1], [1.2, -0.9]), ([0, 0, 3.0, 0, 0], [0.9, 0.2]),
+                      ([0, 0, 0.4, 0.8, -0.3], [1.5, 1.0])):
+        T = R.load_tree()
+        T.math_mpc(list(init), list(tgt), False)
+        assert T.p < 60, T.p
+        cases.append(dict(init=_f(init), target=_f(tgt), origin=[float(T.x_0), float(T.y_0)],
+                          first_threshold=float(T.control_criterion([T.x_0, T.y_0, T.phi_0])),
+                          ticks=int(T.p) - 1, m=int(T.m), recursive=bool(T.recursive),
+                          steps_for_slowing=int(T.steps_for_slowing),
+                          log=[_f(T.ns["result_trajectory_" + k][1:]) for k in ("x", "y", "phi", "v", "beta")]))
+    return dict(meta=_meta(), cost="tree", H=3, cases=cases)
+
+
 def gen_held_single():
     cases = []
     rng = np.random.default_rng(7)
@@ -162,8 +180,11 @@ def main():
     if not R.reference_available():
         raise SystemExit("needs /root/reference (build container only)")
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("pieces", gen_pieces), ("held_single", gen_held_single), ("full_h3", gen_full),
-                     ("held_closed_loop", gen_held_closed_loop)):
+    only = sys.argv[1:]
+    for name, fn in (("pieces", gen_pieces), ("held_single", gen_held_single), ("held_short_loops", gen_held_short_loops),
+                     ("full_h3", gen_full), ("held_closed_loop", gen_held_closed_loop)):
+        if only and name not in only:
+            continue
         data = fn()
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(data, f, indent=None, separators=(",", ":"))

@@ -41,3 +41,52 @@ def test_actual_mode_runs_with_seeded_noise():
     assert len(mt.actual_result_trajectory_x) > 20
     assert mt.is_on_target(mt.actual_result_trajectory_x[-1], mt.actual_result_trajectory_y[-1], mt.x_t, mt.y_t)[0] \
         or mt.recursive
+
+
+def _window_params(max_ticks=200):
+    from diplomjourney_b200 import _native as nat, config
+    return nat, nat.LoopParams.from_config(config, nat.COST_TREE, 3, max_ticks)
+
+
+def test_device_closed_loop_matches_reference_runs(golden):
+    """mpcb_held_closed_loop: whole event-free math_mpc runs on the device vs the reference's own logs
+    (incl. one run that ends in the 'Recursive error' stall)."""
+    nat, params = _window_params()
+    g = golden("held_short_loops")
+    s = nat.Solver(0)
+    cases = g["cases"]
+    r = s.held_closed_loop(params, [c["init"] for c in cases], [c["target"] for c in cases],
+                           [c["origin"] for c in cases], first_threshold=[c["first_threshold"] for c in cases])
+    for i, c in enumerate(cases):
+        ref = np.array(c["log"]).T                      # [ticks][5]
+        assert r["ticks"][i] == ref.shape[0], (i, r["ticks"][i], ref.shape)
+        np.testing.assert_allclose(r["log"][i, :ref.shape[0]], ref, rtol=0, atol=1e-9)
+        assert r["status"][i] == (nat.LOOP_STALLED if c["recursive"] else nat.LOOP_ON_TARGET)
+    s.close()
+
+
+def test_device_closed_loop_batch_equals_per_tick_host_loop():
+    """A batch of random robots: the device-resident loop and the per-tick host loop (math_mpc with the
+    scripted events switched off, every tick one GPU HELD solve) produce the same trajectories."""
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    rng = np.random.default_rng(11)
+    n = 6
+    init = np.zeros((n, 5))
+    init[:, 2] = rng.uniform(-1.0, 1.0, n)
+    init[:, 3] = rng.choice([0.0, 0.3, 0.6], n)
+    ang = init[:, 2] + rng.uniform(-0.6, 0.6, n)
+    dist_ = rng.uniform(0.8, 2.5, n)
+    tgt = np.stack([dist_ * np.cos(ang), dist_ * np.sin(ang)], 1)
+    batch = mt.math_mpc_batch(init, tgt, max_ticks=300)
+    assert set(batch["status"]) <= {0, 1}
+    mt.scripted_events = False
+    for i in range(n):
+        mt.reset_state()
+        mt.x_t, mt.y_t = tgt[i]
+        mt.optimal_criterion = mt.control_criterion([mt.x_0, mt.y_0, mt.phi_0])
+        mt.math_mpc(list(init[i]), list(tgt[i]), False)
+        host = np.array([mt.result_trajectory_x[1:], mt.result_trajectory_y[1:], mt.result_trajectory_phi[1:],
+                         mt.result_trajectory_v[1:], mt.result_trajectory_beta[1:]], dtype=float).T
+        k = batch["ticks"][i]
+        assert k == host.shape[0], (i, k, host.shape)
+        np.testing.assert_allclose(batch["log"][i, :k], host, rtol=0, atol=1e-9)

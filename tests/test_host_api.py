@@ -120,3 +120,16 @@ def test_tree_module_closed_loop_on_oracle_backend(golden):
     assert (mt.p, mt.m, mt.steps_for_slowing, mt.recursive) == (fin["p"], fin["m"], fin["steps_for_slowing"], fin["recursive"])
     assert (mt.x_0, mt.y_0) == pytest.approx((fin["x_0"], fin["y_0"]), abs=1e-9)
     assert mt._backend.calls == 151
+
+
+def test_tree_module_short_runs_on_oracle_backend(golden):
+    """Event-free reference runs (finish before the first scripted event), incl. a 'Recursive error' stall."""
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    for c in golden("held_short_loops")["cases"]:
+        mt.reset_state()
+        mt._backend = OracleBackend()
+        mt.math_mpc(list(c["init"]), list(c["target"]), False)
+        got = np.array([mt.result_trajectory_x[1:], mt.result_trajectory_y[1:], mt.result_trajectory_phi[1:],
+                        mt.result_trajectory_v[1:], mt.result_trajectory_beta[1:]], dtype=float)
+        np.testing.assert_allclose(got, np.array(c["log"]), rtol=0, atol=1e-9)
+        assert (mt.p - 1, mt.m, mt.recursive, mt.steps_for_slowing) == (c["ticks"], c["m"], c["recursive"], c["steps_for_slowing"])

@@ -53,5 +53,31 @@ def timing():
             t = time.perf_counter(); r = s.solve(nat.MODE_HELD, nat.COST_TREE, 3, sc[:, :3], sc[:, 3:5], sc[:, :2]); dt = time.perf_counter() - t
         print(f"HELD S=24321 H=3 N={N} (host API): {dt*1e3:.3f} ms  {N*24321/dt:.3e} rollouts/s stats={s.stats()}")
 
-errs()
-timing()
+def latency():
+    import importlib
+    from diplomjourney_b200 import config
+    V, B = C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0)
+    x = C.random_scenarios(1, 3)[0]
+    for name, fn in (("set_grid S=451", lambda: s.set_grid(V, B, L, DT, VMIN)),
+                     ("HELD solve N=1 S=451 (host API)", lambda: s.solve(nat.MODE_HELD, nat.COST_TREE, 3, x[:3], x[3:5], x[:2]))):
+        fn(); fn()
+        t = time.perf_counter()
+        for _ in range(200): fn()
+        print(f"{name}: {(time.perf_counter()-t)/200*1e6:.1f} us")
+    params = nat.LoopParams.from_config(config, nat.COST_TREE, 3, 256)
+    rng = np.random.default_rng(0)
+    for N in (1, 1024, 16384):
+        init = np.zeros((N, 5)); init[:, 2] = rng.uniform(-1, 1, N)
+        ang = init[:, 2] + rng.uniform(-0.5, 0.5, N); d = rng.uniform(1.0, 4.0, N)
+        tgt = np.stack([d*np.cos(ang), d*np.sin(ang)], 1)
+        for rep in range(2):
+            t = time.perf_counter(); r = s.held_closed_loop(params, init, tgt, [[0.0, 0.0]], first_threshold=1e10); dt = time.perf_counter() - t
+        ticks = int(r["ticks"].sum())
+        print(f"device closed loop N={N}: {dt*1e3:.2f} ms, {ticks} ticks total ({ticks/N:.1f}/robot), {ticks/dt:.3e} MPC solves/s, status counts {np.bincount(r['status'], minlength=4).tolist()}")
+
+if len(sys.argv) > 1 and sys.argv[1] == "latency":
+    latency()
+else:
+    errs()
+    timing()
+    latency()
