@@ -137,6 +137,50 @@ def closed_form_cpu(wl):
                 note="oracle/mpc_oracle.c: float64 closed form with prefix sharing, pthreads, 1 solve")
 
 
+def held_metrics(solver, nat, C, device_index):
+    """MPC solves/s of the online (HELD, CoordinateTree-pruned) controller -- the other half of the
+    BASELINE metric: (a) whole closed loops resident on the device for a batch of robots,
+    (b) one tick through the reference-API call on host buffers, (c) a 1,024-robot batch on the
+    FULL scripts' 201x121 grid (S=24,321 candidates per solve)."""
+    from diplomjourney_b200 import config
+    out = {}
+    rng = np.random.default_rng(0)
+    n = 4096
+    params = nat.LoopParams.from_config(config, nat.COST_TREE, 3, 256)
+    init = np.zeros((n, 5)); init[:, 2] = rng.uniform(-1, 1, n)
+    ang = init[:, 2] + rng.uniform(-0.5, 0.5, n); d = rng.uniform(1.0, 4.0, n)
+    tgt = np.stack([d * np.cos(ang), d * np.sin(ang)], 1)
+    for _ in range(3):
+        t = time.perf_counter()
+        r = solver.held_closed_loop(params, init, tgt, [[0.0, 0.0]], first_threshold=1e10)
+        dt = time.perf_counter() - t
+    out["closed_loop_batch"] = dict(robots=n, ticks=int(r["ticks"].sum()), seconds=dt,
+                                    solves_per_s=float(r["ticks"].sum() / dt), S_max=451,
+                                    note="mpcb_held_closed_loop_host: whole math_mpc loops on the device, host wall incl. copies")
+    V, B = C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0)
+    x = C.random_scenarios(1, 3)[0]
+    reps = 300
+    solver.set_grid(V, B, C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
+    solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, x[:3], x[3:5], x[:2])
+    t = time.perf_counter()
+    for _ in range(reps):
+        solver.set_grid(V, B, C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
+        solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, x[:3], x[3:5], x[:2])
+    dt = (time.perf_counter() - t) / reps
+    out["single_tick_host_api"] = dict(us_per_solve=dt * 1e6, solves_per_s=1.0 / dt, S=len(V) * len(B),
+                                       note="set_grid + solve per tick, host buffers, 1 H2D + 1 kernel + 1 D2H")
+    Vf, Bf = C.grid_full_default()
+    solver.set_grid(Vf, Bf, C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
+    sc = C.random_scenarios(1024, 1)
+    for _ in range(3):
+        t = time.perf_counter()
+        solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, sc[:, :3], sc[:, 3:5], sc[:, :2])
+        dt = time.perf_counter() - t
+    out["batch_201x121"] = dict(robots=1024, S=int(Vf.size * Bf.size), seconds=dt, solves_per_s=1024 / dt,
+                                rollouts_per_s=1024 * Vf.size * Bf.size / dt)
+    return out
+
+
 def run_reference(args):
     wl = workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
@@ -269,6 +313,7 @@ def run_gpu(args):
         if ok != chk:
             raise SystemExit("PARITY FAILURE in bench: " + parity)
 
+    held = held_metrics(solver, nat, C, local) if rank == 0 else None
     if rank == 0:
         pk = peaks()
         clk_hz = pk["sm_max_mhz"] * 1e6
@@ -288,16 +333,18 @@ def run_gpu(args):
                 achieved=per_gpu_rate * mufu_a / 1e12, peak=mufu_peak / 1e12,
                 frac=per_gpu_rate * mufu_a / mufu_peak, traffic=None,
                 accounting="A: (2H+1) MUFU per rollout, one-thread-per-leaf design (SURVEY 8d); the prefix kernel "
-                           "executes 2 MUFU + 15 FP32-pipe instr per rollout, so frac>1 under A is expected",
-                executed=dict(mufu_per_rollout=2, fp32_instr_per_rollout=15,
-                              mufu_frac=per_gpu_rate * 2 / mufu_peak, fp32_frac=per_gpu_rate * 15 / fp32_peak),
+                           "shares prefixes and executes 1.5 MUFU + 13.5 FP32 lane-ops (17 issue cycles) per rollout "
+                           "(SASS of prefix_min_loop_far2), so frac>1 under A is expected",
+                executed=dict(mufu_per_rollout=1.5, fp32_ops_per_rollout=13.5, issue_cycles_per_rollout=17.0,
+                              mufu_frac=per_gpu_rate * 1.5 / mufu_peak, fp32_frac=per_gpu_rate * 13.5 / fp32_peak,
+                              issue_frac=per_gpu_rate * 17.0 / fp32_peak),
                 hbm_gbs=(h2d + d2h) / (kern_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
                 peak_src=f"{pk['src']} sm_max_mhz={pk['sm_max_mhz']:.0f} x {SM_COUNT} SMs x {MUFU_PER_CLK_SM} MUFU/clk/SM",
                 kernel="prefix_kernel<1,true> (pass 1)", kernel_ms_per_step=kern_ms),
             e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      solves_per_s=n * world * args.steps / float(te[0])),
             gpu_launches=stats["kernel_launches"] * args.steps,
-            clocks=clocks, parity=parity,
+            clocks=clocks, parity=parity, held=held,
             refine=dict(segments=stats["refine_segments"], candidates=stats["refine_candidates"]),
         )
         if world == 1 and not args.no_cpu:

@@ -22,6 +22,7 @@ cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, un
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
+cudaError_t launch_held_small(cudaStream_t, const SmallArgs &);
 }  // namespace mpcb
 
 using namespace mpcb;
@@ -63,17 +64,22 @@ struct mpcb_handle_s {
     cudaStream_t stream = nullptr;
     std::string err;
     // grid
-    bool have_grid = false;
+    bool have_grid = false, tables_ready = false;
+    std::vector<double> hv, hb;         // host copy of the raw grids
+    double L = 0, delta_t = 0, v_min = 0, v_slow = 0;
     GridTables g{};
     DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, ctl32, ctl32_slow;
     // options
     double tol_scale = 1.0;
     int algo = MPCB_ALGO_AUTO;
     int refine = 1;
+    int small_path = 1;   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
     DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock;
     DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
-    DevBuf loop_log, loop_ticks, loop_status;
+    DevBuf loop_log, loop_ticks, loop_status, small_in, small_out;
+    void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
+    size_t pin_in_cap = 0, pin_out_cap = 0;
     mpcb_stats stats{};
     unsigned long long last_counters_pending = 0;
 };
@@ -162,73 +168,11 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
 
 }  // namespace
 
-extern "C" {
-
-int mpcb_version(void) { return 100; }
-
-int mpcb_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-    return n;
-}
-
-int mpcb_create(int device_ordinal, mpcb_handle **out) {
-    if (!out) return MPCB_ERR_INVALID;
-    *out = nullptr;
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return MPCB_ERR_NO_DEVICE;
-    if (device_ordinal < 0 || device_ordinal >= n) return MPCB_ERR_INVALID;
-    mpcb_handle *h = new mpcb_handle_s();
-    h->device = device_ordinal;
-    if (cudaSetDevice(device_ordinal) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete h;
-        return MPCB_ERR_CUDA;
-    }
-    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device_ordinal);
-    *out = h;
-    return MPCB_OK;
-}
-
-int mpcb_destroy(mpcb_handle *h) {
-    if (!h) return MPCB_OK;
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
-                      &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
-                      &h->lock, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
-                      &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
-                      &h->loop_status})
-        b->release();
-    cudaStreamDestroy(h->stream);
-    delete h;
-    return MPCB_OK;
-}
-
-const char *mpcb_last_error(const mpcb_handle *h) { return h ? h->err.c_str() : "null handle"; }
-void *mpcb_stream(mpcb_handle *h) { return h ? (void *)h->stream : nullptr; }
-
-int mpcb_sync(mpcb_handle *h) {
-    if (!h) return MPCB_ERR_INVALID;
-    CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
-    return MPCB_OK;
-}
-
-int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
-    if (!h || !name) return MPCB_ERR_INVALID;
-    if (!strcmp(name, "tol_scale")) h->tol_scale = value;
-    else if (!strcmp(name, "algo")) h->algo = (int)value;
-    else if (!strcmp(name, "refine")) h->refine = value != 0.0;
-    else return fail(h, MPCB_ERR_INVALID, "unknown option '%s'", name);
-    return MPCB_OK;
-}
-
-int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, int nb, double L, double delta_t,
-                  double v_min) {
-    if (!h || (!v && nv) || (!beta && nb) || nv < 0 || nb < 0) return fail(h, MPCB_ERR_INVALID, "set_grid: bad arguments");
-    if (nv == 0 || nb == 0) { h->have_grid = false; return fail(h, MPCB_ERR_EMPTY_GRID, "empty control grid"); }
-    if ((long long)nv * nb > (1LL << 30)) return fail(h, MPCB_ERR_TOO_LARGE, "grid too large");
+static int ensure_tables(mpcb_handle *h) {
+    if (h->tables_ready) return MPCB_OK;
+    const double *v = h->hv.data(), *beta = h->hb.data();
+    const int nv = (int)h->hv.size(), nb = (int)h->hb.size();
+    const double L = h->L, delta_t = h->delta_t, v_min = h->v_min;
     CK(cudaSetDevice(h->device));
     const int S = nv * nb;
     std::vector<double4> t64(S), t64s(S);
@@ -296,7 +240,92 @@ int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, i
     g.leaf32p = h->leaf32p.as<float4>();
     g.ctl32 = h->ctl32.as<float2>(); g.ctl32_slow = h->ctl32_slow.as<float2>();
     g.S = S; g.nb = nb; g.dt = delta_t; g.smax = smax; g.dphimax = dphimax;
+    h->tables_ready = true;
+    return MPCB_OK;
+}
+
+
+extern "C" {
+
+int mpcb_version(void) { return 100; }
+
+int mpcb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int mpcb_create(int device_ordinal, mpcb_handle **out) {
+    if (!out) return MPCB_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return MPCB_ERR_NO_DEVICE;
+    if (device_ordinal < 0 || device_ordinal >= n) return MPCB_ERR_INVALID;
+    mpcb_handle *h = new mpcb_handle_s();
+    h->device = device_ordinal;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return MPCB_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device_ordinal);
+    *out = h;
+    return MPCB_OK;
+}
+
+int mpcb_destroy(mpcb_handle *h) {
+    if (!h) return MPCB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
+                      &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
+                      &h->lock, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
+                      &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
+                      &h->loop_status, &h->small_in, &h->small_out})
+        b->release();
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MPCB_OK;
+}
+
+const char *mpcb_last_error(const mpcb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+void *mpcb_stream(mpcb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int mpcb_sync(mpcb_handle *h) {
+    if (!h) return MPCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCB_OK;
+}
+
+int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
+    if (!h || !name) return MPCB_ERR_INVALID;
+    if (!strcmp(name, "tol_scale")) h->tol_scale = value;
+    else if (!strcmp(name, "algo")) h->algo = (int)value;
+    else if (!strcmp(name, "refine")) h->refine = value != 0.0;
+    else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
+    else return fail(h, MPCB_ERR_INVALID, "unknown option '%s'", name);
+    return MPCB_OK;
+}
+
+int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, int nb, double L, double delta_t,
+                  double v_min) {
+    if (!h || (!v && nv) || (!beta && nb) || nv < 0 || nb < 0) return fail(h, MPCB_ERR_INVALID, "set_grid: bad arguments");
+    if (nv == 0 || nb == 0) { h->have_grid = false; return fail(h, MPCB_ERR_EMPTY_GRID, "empty control grid"); }
+    if ((long long)nv * nb > (1LL << 30)) return fail(h, MPCB_ERR_TOO_LARGE, "grid too large");
+    // Host-side only: the per-control tables are built and uploaded on first use by a kernel that
+    // needs them (ensure_tables); the low-latency HELD path works from the raw grids.
+    h->hv.assign(v, v + nv);
+    h->hb.assign(beta, beta + nb);
+    h->L = L; h->delta_t = delta_t; h->v_min = v_min;
+    double vmin_grid = v[0];
+    for (int i = 1; i < nv; ++i) vmin_grid = std::min(vmin_grid, v[i]);
+    h->v_slow = vmin_grid > v_min ? vmin_grid : v_min;   // math_model_tree.py:312-316
+    h->g.S = nv * nb; h->g.nb = nb; h->g.dt = delta_t;
     h->have_grid = true;
+    h->tables_ready = false;
     return MPCB_OK;
 }
 
@@ -313,8 +342,10 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     if (N == 0) return MPCB_OK;
     if (!state || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
     CK(cudaSetDevice(h->device));
+    int rc = ensure_tables(h);
+    if (rc) return rc;
     Plan pl;
-    int rc = make_plan(h, mode, H, N, i0_begin, i0_end, MPCB_ALGO_AUTO, pl);
+    rc = make_plan(h, mode, H, N, i0_begin, i0_end, MPCB_ALGO_AUTO, pl);
     if (rc) return rc;
 
     LaunchArgs a;
@@ -390,6 +421,62 @@ int mpcb_get_stats(mpcb_handle *h, mpcb_stats *out) {
     return MPCB_OK;
 }
 
+// Low-latency HELD path of the host API: one pinned staging buffer in, ONE kernel (float64, straight
+// from the raw grids), one staging buffer out -- 1 H2D + 1 launch + 1 D2H + 1 sync per call.
+static int solve_held_small(mpcb_handle *h, int cost_kind, int H, int64_t N, const double *state,
+                            const double *target, const double *origin, const double *threshold,
+                            const uint8_t *flags, double *best_cost, int64_t *best_index, double *best_traj,
+                            double *first_control) {
+    cudaStream_t st = h->stream;
+    const size_t nv = h->hv.size(), nb = h->hb.size();
+    const size_t n_in = nv + nb + (size_t)N * (3 + 2 + 2 + (threshold ? 1 : 0) + (flags ? 1 : 0));
+    const size_t n_out = (size_t)N * (1 + 1 + 3 * H + 2);
+    auto pinned = [&](void *&p, size_t &cap, size_t bytes) -> cudaError_t {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes * 2);
+        if (e == cudaSuccess) cap = bytes * 2;
+        return e;
+    };
+    CK(pinned(h->pin_in, h->pin_in_cap, n_in * 8));
+    CK(pinned(h->pin_out, h->pin_out_cap, n_out * 8));
+    CK(h->small_in.ensure(n_in * 8));
+    CK(h->small_out.ensure(n_out * 8));
+    double *w = (double *)h->pin_in;
+    const double *d = h->small_in.as<double>();
+    SmallArgs a{};
+    auto put = [&](const double *src, size_t cnt) { const double *dev = d + (w - (double *)h->pin_in); memcpy(w, src, cnt * 8); w += cnt; return dev; };
+    a.v = put(h->hv.data(), nv);
+    a.beta = put(h->hb.data(), nb);
+    a.state = put(state, 3 * (size_t)N);
+    a.target = put(target, 2 * (size_t)N);
+    a.origin = put(origin, 2 * (size_t)N);
+    if (threshold) a.threshold = put(threshold, (size_t)N);
+    if (flags) {
+        a.flags = d + (w - (double *)h->pin_in);
+        for (int64_t i = 0; i < N; ++i) *w++ = (flags[i] & MPCB_FLAG_SLOW) ? 1.0 : 0.0;
+    }
+    double *o = h->small_out.as<double>();
+    a.out_cost = o; a.out_index = (long long *)(o + N); a.out_traj = o + 2 * N; a.out_ctl = o + 2 * N + 3 * (size_t)H * N;
+    a.L = h->L; a.delta_t = h->delta_t; a.v_slow = h->v_slow;
+    a.nv = (int)nv; a.nb = (int)nb; a.H = H; a.cost_kind = cost_kind; a.N = N;
+    CK(cudaMemcpyAsync(h->small_in.p, h->pin_in, n_in * 8, cudaMemcpyHostToDevice, st));
+    CK(launch_held_small(st, a));
+    CK(cudaMemcpyAsync(h->pin_out, h->small_out.p, n_out * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double *r = (const double *)h->pin_out;
+    if (best_cost) memcpy(best_cost, r, 8 * (size_t)N);
+    if (best_index) memcpy(best_index, r + N, 8 * (size_t)N);
+    if (best_traj) memcpy(best_traj, r + 2 * N, 8 * 3 * (size_t)H * N);
+    if (first_control) memcpy(first_control, r + 2 * N + 3 * (size_t)H * N, 8 * 2 * (size_t)N);
+    h->stats = mpcb_stats{};
+    h->stats.units = h->stats.leaves_per_solve = (int64_t)(nv * nb);
+    h->stats.algo = MPCB_ALGO_LEAFWALK;
+    h->stats.kernel_launches = 1;
+    return MPCB_OK;
+}
+
 int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
                           const double *target, const double *origin, const double *threshold,
                           const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
@@ -398,7 +485,13 @@ int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_
     if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
     if (!state || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
     if (H < 1 || H > MPCB_MAX_H) return fail(h, MPCB_ERR_INVALID, "H=%d out of range [1,%d]", H, MPCB_MAX_H);
+    if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
+    if ((cost_kind != MPCB_COST_MM && cost_kind != MPCB_COST_TREE) || (mode != MPCB_MODE_FULL && mode != MPCB_MODE_HELD))
+        return fail(h, MPCB_ERR_INVALID, "bad mode/cost");
     CK(cudaSetDevice(h->device));
+    if (mode == MPCB_MODE_HELD && h->small_path && h->g.S <= 4096 && h->hb.size() <= 4096 && N <= 8192)
+        return solve_held_small(h, cost_kind, H, N, state, target, origin, threshold, flags, best_cost, best_index,
+                                best_traj, first_control);
     cudaStream_t st = h->stream;
     CK(h->in_state.ensure(sizeof(double) * 3 * N));
     CK(h->in_target.ensure(sizeof(double) * 2 * N));
@@ -445,8 +538,10 @@ int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int al
     if (count == 0) return MPCB_OK;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    int rc = ensure_tables(h);
+    if (rc) return rc;
     Plan pl;
-    int rc = make_plan(h, mode, H, 1, 0, -1, algo == MPCB_ALGO_AUTO ? MPCB_ALGO_LEAFWALK : algo, pl);
+    rc = make_plan(h, mode, H, 1, 0, -1, algo == MPCB_ALGO_AUTO ? MPCB_ALGO_LEAFWALK : algo, pl);
     if (rc) return rc;
     if ((unsigned long long)(leaf_begin + count) > pl.leaves_per_solve)
         return fail(h, MPCB_ERR_INVALID, "dump range exceeds the %llu leaves of the tree", pl.leaves_per_solve);

@@ -190,6 +190,71 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One HELD solve per CTA straight from the raw grids (v[nv], beta[nb]) in float64: the low-latency
+// path of the per-tick host API (S <= a few thousand candidates; no tables, no fp32 stage, one launch).
+__global__ void __launch_bounds__(kLoopThreads) held_small_kernel(const SmallArgs a) {
+    extern __shared__ double s_tan[];
+    __shared__ double s_J[kLoopThreads / 32];
+    __shared__ int s_j[kLoopThreads / 32];
+    const int tid = threadIdx.x;
+    const long long n = blockIdx.x;
+    mpcb_loop_params p{};
+    p.L = a.L; p.delta_t = a.delta_t; p.H = a.H;
+    LoopCost cost;
+    cost.xt = a.target[2 * n]; cost.yt = a.target[2 * n + 1];
+    cost.ox = a.origin[2 * n]; cost.oy = a.origin[2 * n + 1];
+    cost.A = cost.yt - cost.oy; cost.B = cost.xt - cost.ox;
+    cost.C = cost.xt * cost.oy - cost.yt * cost.ox;
+    cost.norm = sqrt(cost.A * cost.A + cost.B * cost.B);
+    cost.theta = atan(cost.xt / cost.yt);
+    cost.kind = a.cost_kind;
+    const bool slow = a.flags && (a.flags[n] != 0.0);
+    for (int i = tid; i < a.nb; i += kLoopThreads) s_tan[i] = tan(a.beta[i]);
+    __syncthreads();
+    const double x0 = a.state[3 * n], y0 = a.state[3 * n + 1], phi0 = a.state[3 * n + 2];
+    const int S = a.nv * a.nb;
+    double bJ = INFINITY; int bj = -1;
+    for (int c = tid; c < S; c += kLoopThreads) {
+        const int iv = c / a.nb, ib = c - iv * a.nb;
+        const double v = slow ? a.v_slow : a.v[iv];
+        double x = x0, y = y0, phi = phi0;
+        loop_walk(p, v, s_tan[ib], x, y, phi, nullptr);
+        lex_min_d(bJ, bj, cost(x, y, phi), c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oJ = __shfl_xor_sync(0xffffffffu, bJ, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        lex_min_d(bJ, bj, oJ, oj);
+    }
+    if ((tid & 31) == 0) { s_J[tid >> 5] = bJ; s_j[tid >> 5] = bj; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < kLoopThreads / 32; ++i) lex_min_d(bJ, bj, s_J[i], s_j[i]);
+        const double thr = a.threshold ? a.threshold[n] : INFINITY;
+        double *traj = a.out_traj + (size_t)n * 3 * a.H;
+        if (bj >= 0) {
+            const int iv = bj / a.nb, ib = bj - iv * a.nb;
+            const double v = slow ? a.v_slow : a.v[iv];
+            double x = x0, y = y0, phi = phi0;
+            loop_walk(p, v, s_tan[ib], x, y, phi, traj);
+            a.out_cost[n] = bJ;
+            a.out_index[n] = bJ < thr ? bj : -1;
+            a.out_ctl[2 * n] = v; a.out_ctl[2 * n + 1] = a.beta[ib];
+        } else {
+            a.out_cost[n] = NAN; a.out_index[n] = -1;
+            for (int k = 0; k < 3 * a.H; ++k) traj[k] = NAN;
+            a.out_ctl[2 * n] = NAN; a.out_ctl[2 * n + 1] = NAN;
+        }
+    }
+}
+
+cudaError_t launch_held_small(cudaStream_t st, const SmallArgs &a) {
+    held_small_kernel<<<(unsigned)a.N, kLoopThreads, sizeof(double) * a.nb, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_held_loop(cudaStream_t st, const LoopArgs &a, int sms) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, held_loop_kernel, kLoopThreads, 0) != cudaSuccess || per_sm < 1)

@@ -104,4 +104,14 @@ struct LoopArgs {
     int *out_ticks, *out_status;
 };
 
+// one-launch float64 HELD solve from the raw grids (mpcb_loop.cu); all pointers are device
+struct SmallArgs {
+    const double *v, *beta;            // raw grids
+    const double *state, *target, *origin, *threshold, *flags;   // flags as doubles (0 / non-0), nullable
+    double *out_cost; long long *out_index; double *out_traj, *out_ctl;
+    double L, delta_t, v_slow;
+    int nv, nb, H, cost_kind;
+    long long N;
+};
+
 }  // namespace mpcb

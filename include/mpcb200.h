@@ -86,7 +86,8 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
                   double L, double delta_t, double v_min);
 
 /* Options: "tol_scale" (candidate-window multiplier, default 1), "algo" (MPCB_ALGO_*),
- * "refine" (1 = float64 re-evaluation of near-minimal leaves, default; 0 = fp32 winner). */
+ * "refine" (1 = float64 re-evaluation of near-minimal leaves, default; 0 = fp32 winner),
+ * "small_path" (1 = host-API HELD solves with <= 4096 candidates run as one float64 launch, default). */
 MPCB_API int mpcb_set_option(mpcb_handle *h, const char *name, double value);
 
 /* Batch of N independent MPC solves sharing the grid.  Replaces N calls of

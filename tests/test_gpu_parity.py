@@ -59,8 +59,11 @@ def test_full_golden_reference_outputs(solver, golden, algo):
         solver.set_option("algo", nat.ALGO_AUTO)
 
 
-def test_held_golden_reference_outputs(solver, golden):
+@pytest.mark.parametrize("small_path", [1, 0])
+def test_held_golden_reference_outputs(solver, golden, small_path):
+    """small_path=1: one-launch float64 kernel; 0: the general fp32 leafwalk + float64 refinement pipeline."""
     g = golden("held_single")
+    solver.set_option("small_path", small_path)
     for c in g["cases"]:
         solver.set_grid(c["vector_v"], c["vector_beta"], L, DT, VMIN)
         r = solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, c["state"], c["target"], c["origin"],
@@ -68,6 +71,8 @@ def test_held_golden_reference_outputs(solver, golden):
         ret = list(r["traj"][0, 0]) + list(r["first_control"][0])
         np.testing.assert_allclose(ret, c["ret"], rtol=0, atol=1e-12)
         np.testing.assert_allclose(r["traj"][0], np.array(c["traj"]), rtol=0, atol=1e-12)
+        assert solver.stats()["kernel_launches"] == (1 if small_path else 5)
+    solver.set_option("small_path", 1)
 
 
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
