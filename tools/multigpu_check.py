@@ -36,20 +36,29 @@ lo, hi = D.shard_range(s.S, world, rank)
 oc = torch.empty(1, dtype=torch.float64, device="cuda"); oi = torch.empty(1, dtype=torch.int64, device="cuda")
 st = torch.tensor(x[:3].copy(), device="cuda"); tg = torch.tensor(x[3:5].copy(), device="cuda"); og = torch.tensor(x[:2].copy(), device="cuda")
 torch.cuda.synchronize()
-H = 5   # 256^5 = 1.1e12 leaves, split over the ranks (config 5 is H=6: 256x this)
-t0 = time.perf_counter()
-s.solve_device(nat.MODE_FULL, nat.COST_MM, H, 1, st.data_ptr(), tg.data_ptr(), og.data_ptr(), 0, 0, oc.data_ptr(), oi.data_ptr(), 0, 0, i0_range=(lo, hi))
-comm.allreduce_min(oc.data_ptr(), oi.data_ptr())
-s.sync()
-dt = time.perf_counter() - t0
-tt = torch.tensor([dt], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-rec = torch.stack([oc, oi.double()]).cpu().numpy().ravel()
-allrec = [None] * world
-dist.all_gather_object(allrec, (float(rec[0]), int(oi[0])))
-ok = ok and all(a == allrec[0] for a in allrec)
+ext = torch.cuda.ExternalStream(s.stream)
+for H in [int(h) for h in os.environ.get("MPCB_SPLIT_H", "4,5").split(",")]:
+    # 256^5 = 1.1e12 leaves; 256^6 = 2.8e14 leaves is BASELINE config 5
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    with torch.cuda.stream(ext):
+        ev0.record()
+        s.solve_device(nat.MODE_FULL, nat.COST_MM, H, 1, st.data_ptr(), tg.data_ptr(), og.data_ptr(), 0, 0, oc.data_ptr(), oi.data_ptr(), 0, 0, i0_range=(lo, hi))
+        comm.allreduce_min(oc.data_ptr(), oi.data_ptr())
+        ev1.record()
+    s.sync(); torch.cuda.synchronize()
+    tt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    allrec = [None] * world
+    dist.all_gather_object(allrec, (float(oc[0]), int(oi[0])))
+    ok = ok and all(a == allrec[0] for a in allrec)
+    st_ = s.stats()
+    if rank == 0:
+        leaves = s.S ** H
+        print(f"world={world} split-tree H={H} leaves={leaves:.3e} record={allrec[0]} time={float(tt[0]):.4f}s "
+              f"rate={leaves/float(tt[0]):.3e} rollouts/s refine(seg={st_['refine_segments']},cand={st_['refine_candidates']}) "
+              f"[first H includes NCCL connection setup]", flush=True)
 if rank == 0:
-    leaves = s.S ** H
-    print(f"world={world} parity={'OK' if ok else 'FAIL'} native-nccl record={allrec[0]} H={H} leaves={leaves:.3e} time={float(tt[0]):.3f}s rate={leaves/float(tt[0]):.3e} rollouts/s", flush=True)
+    print(f"world={world} parity={'OK' if ok else 'FAIL'}", flush=True)
 comm.close(); s.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
