@@ -228,6 +228,7 @@ def run_gpu(args):
     leaves_per_solve = S ** Hh
     solver = nat.Solver(local)
     solver.set_grid(wl["V"], wl["B"], C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
+    solver.set_option("algo", {"auto": nat.ALGO_AUTO, "prefix": nat.ALGO_PREFIX, "leafwalk": nat.ALGO_LEAFWALK}[args.algo])
 
     # each rank owns its own robots (contiguous ranges of the global batch): no data-path collective
     scen = C.random_scenarios(n * world, wl["seed"])[rank * n:(rank + 1) * n]
@@ -313,7 +314,8 @@ def run_gpu(args):
         if ok != chk:
             raise SystemExit("PARITY FAILURE in bench: " + parity)
 
-    held = held_metrics(solver, nat, C, local) if rank == 0 else None
+    solver.set_option("algo", nat.ALGO_AUTO)
+    held = held_metrics(solver, nat, C, local) if rank == 0 and args.algo == "auto" else None
     if rank == 0:
         pk = peaks()
         clk_hz = pk["sm_max_mhz"] * 1e6
@@ -341,7 +343,8 @@ def run_gpu(args):
                               issue_frac=per_gpu_rate * 17.0 / fp32_peak),
                 hbm_gbs=(h2d + d2h) / (kern_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
                 peak_src=f"{pk['src']} sm_max_mhz={pk['sm_max_mhz']:.0f} x {SM_COUNT} SMs x {MUFU_PER_CLK_SM} MUFU/clk/SM",
-                kernel="prefix_kernel<1,true> (pass 1)", kernel_ms_per_step=kern_ms),
+                kernel=("leafwalk_kernel<1,true,1>" if stats["algo"] == nat.ALGO_LEAFWALK else "prefix_kernel<1,true>") + " (pass 1)",
+                kernel_ms_per_step=kern_ms),
             e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      solves_per_s=n * world * args.steps / float(te[0])),
             gpu_launches=stats["kernel_launches"] * args.steps,
@@ -365,6 +368,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--algo", default="auto", choices=["auto", "prefix", "leafwalk"],
+                    help="expansion kernel: prefix (default for this workload) or the one-thread-per-leaf design")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

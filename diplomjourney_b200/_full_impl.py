@@ -117,6 +117,15 @@ def install(g, placeholder_trajectory):
         best = g["optimal_trajectory"][0][0]
         return [best[0], best[1], best[2], best[3], best[4]]
 
+    def leaf_cloud(_initial_x, _initial_y, _initial_phi, leaf_begin=0, count=None):
+        """Terminal (x, y) and cost of every leaf in enumeration order -- the data behind the
+        reference's green scatter of ``third_field_x/y`` (math_model.py:192-193,204).  Small trees
+        only (16 bytes per leaf come back to the host)."""
+        xy, cost = _solver().dump_leaves(_native.MODE_FULL, _native.COST_MM, g["prediction_horizon"],
+                                         [_initial_x, _initial_y, _initial_phi], [g["x_t"], g["y_t"]],
+                                         [g["x_0"], g["y_0"]], leaf_begin=leaf_begin, count=count)
+        return xy[:, 0], xy[:, 1], cost
+
     def run_scenario(max_ticks=None, verbose=False):
         """The closed loop of math_model.py:234-254: tick until on target, stop after the
         position repeated twice ("Recursive error")."""

@@ -47,6 +47,16 @@ struct DevBuf {
 
 constexpr unsigned long long kSegCap = 1ULL << 22;
 
+void fastdiv32_init(FastDiv32 &f, unsigned long long d64) {
+    unsigned d = (unsigned)d64;
+    f.d = d;
+    if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
+    unsigned l = 0;
+    while ((l < 32) && ((1ULL << l) < d)) ++l;
+    f.m = (unsigned)((((1ULL << l) - d) << 32) / d) + 1u;
+    f.sh1 = 1; f.sh2 = l - 1;
+}
+
 void fastdiv_init(FastDiv64 &f, unsigned long long d) {
     f.d = d;
     if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
@@ -159,11 +169,15 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
     a.mode = mode; a.H = H; a.cost_kind = cost_kind; a.refine = h->refine;
     a.N = N;
     unsigned long long S = (unsigned long long)h->g.S, pw = 1;
+    a.idx32 = (!pl.prefix && pl.u_end < (1ULL << 32)) ? 1 : 0;
     for (int k = H - 1; k >= 0; --k) {   // fd[k].d = S^(H-1-k)
         fastdiv_init(a.fd[k], pw);
+        if (a.idx32) fastdiv32_init(a.fd32[k], pw);
         if (mode == MPCB_MODE_FULL) pw *= S;
     }
     a.u_begin = pl.u_begin; a.u_end = pl.u_end;
+    a.tile_units = pl.prefix ? kThreads : kThreads * kLeafPerThread;
+    a.lw_smem = (!pl.prefix && mode == MPCB_MODE_FULL && h->g.S <= 4096) ? 1 : 0;
 }
 
 }  // namespace
@@ -351,7 +365,7 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     LaunchArgs a;
     fill_args(h, a, mode, cost_kind, H, N, pl);
     const unsigned long long units = pl.u_end - pl.u_begin;
-    a.tiles_per_solve = (units + kThreads - 1) / kThreads;
+    a.tiles_per_solve = (units + a.tile_units - 1) / a.tile_units;
     unsigned __int128 all_tiles = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
     unsigned long long tps = (unsigned long long)((all_tiles + kSegCap - 1) / kSegCap);
     if (tps < 1) tps = 1;

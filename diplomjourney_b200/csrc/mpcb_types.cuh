@@ -32,6 +32,19 @@ struct FastDiv64 {
 #endif
 };
 
+// 32-bit flavour (indices below 2^32): 5 instructions per quotient instead of ~15
+struct FastDiv32 {
+    unsigned m, d, sh1, sh2;
+#ifdef __CUDACC__
+    __device__ __forceinline__ unsigned div(unsigned n) const {
+        unsigned t = __umulhi(m, n);
+        return (t + ((n - t) >> sh1)) >> sh2;
+    }
+#endif
+};
+
+constexpr int kLeafPerThread = 8;  // leafwalk: leaves per thread per tile (tile = kThreads * kLeafPerThread leaves)
+
 // Per control grid. c = iv*nb + ib.
 struct GridTables {
     // float64, for the depth-(H-1) prefix walk and the exact re-evaluation
@@ -75,6 +88,10 @@ struct LaunchArgs {
     GridTables g;
     const SolveParams *sp;
     FastDiv64 fd[kMaxH];        // fd[k].d = S^(H-1-k)
+    FastDiv32 fd32[kMaxH];      // same divisors, valid when idx32 != 0 (every index and divisor < 2^32)
+    int idx32;
+    int lw_smem;                // leafwalk FULL: stage ctl32 in shared memory (S <= 4096)
+    unsigned tile_units;        // units per tile: kThreads (prefix) or kThreads*kLeafPerThread (leafwalk)
     int mode, H, cost_kind, refine;
     long long N;
     unsigned long long u_begin, u_end;     // unit range of every solve (leaves or depth-(H-1) nodes)

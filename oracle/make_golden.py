@@ -117,6 +117,22 @@ def gen_held_short_loops():
     return dict(meta=_meta(), cost="tree", H=3, cases=cases)
 
 
+def gen_held_actual():
+    """math_mpc(..., isActual=True) (math_model_tree.py:580-629): actuator noise from numpy.random
+    (what ``random`` is after the reference's ``from scipy import *``), seeded, plus the operator
+    events at ticks 1/60/90/110."""
+    cases = []
+    for seed in (5, 11):
+        T = R.load_tree()
+        np.random.seed(seed)
+        T.math_mpc([0, 0, 0, 0, 0], [2, 3], True)
+        cases.append(dict(seed=seed, p=int(T.p), m=int(T.m), recursive=bool(T.recursive),
+                          log={k: _f(T.ns[k]) for k in ("actual_result_trajectory_x", "actual_result_trajectory_y",
+                                                        "actual_result_trajectory_phi", "actual_result_trajectory_v",
+                                                        "actual_result_trajectory_beta")}))
+    return dict(meta=_meta(), call="np.random.seed(seed); math_mpc([0,0,0,0,0],[2,3],True)", cases=cases)
+
+
 def gen_held_single():
     cases = []
     rng = np.random.default_rng(7)
@@ -182,6 +198,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("pieces", gen_pieces), ("held_single", gen_held_single), ("held_short_loops", gen_held_short_loops),
+                     ("held_actual", gen_held_actual),
                      ("full_h3", gen_full), ("held_closed_loop", gen_held_closed_loop)):
         if only and name not in only:
             continue

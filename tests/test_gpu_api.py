@@ -90,3 +90,32 @@ def test_device_closed_loop_batch_equals_per_tick_host_loop():
         k = batch["ticks"][i]
         assert k == host.shape[0], (i, k, host.shape)
         np.testing.assert_allclose(batch["log"][i, :k], host, rtol=0, atol=1e-9)
+
+
+def test_actual_mode_matches_reference_seeded_runs(golden):
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    for c in golden("held_actual")["cases"]:
+        mt.reset_state()
+        mt.x_0, mt.y_0, mt.phi_0 = 0, 0, 0
+        np.random.seed(c["seed"])
+        mt.math_mpc([0, 0, 0, 0, 0], [2, 3], True)
+        for key, ref in c["log"].items():
+            np.testing.assert_allclose(np.array(getattr(mt, key), dtype=float), ref, rtol=0, atol=1e-9, err_msg=key)
+        assert (mt.p, mt.m) == (c["p"], c["m"])
+
+
+def test_full_module_leaf_cloud():
+    from oracle import closed_form as C
+    rm = importlib.import_module("diplomjourney_b200.run_math_model")
+    rm._backend = None
+    rm._grid_key = None
+    rm.vector_v, rm.vector_beta = np.array([0.0, 0.4, 0.7, 1.0]), np.round(np.radians([-60, -30, 0, 30, 60]), 3)
+    rm.reset_scenario(0.5, -1.0, 0.3, 3.0, 2.0)
+    x, y, J = rm.leaf_cloud(0.5, -1.0, 0.3)
+    Jo, xo, yo, _ = C.full_leaf_costs([0.5, -1.0, 0.3], (3.0, 2.0), (0.5, -1.0), rm.vector_v, rm.vector_beta, 3,
+                                      C.COST_MM, return_xy=True)
+    assert x.shape == (20 ** 3,)
+    np.testing.assert_allclose(x, xo, atol=2e-6)
+    np.testing.assert_allclose(y, yo, atol=2e-6)
+    ok = Jo < 1e7
+    np.testing.assert_allclose(J[ok], Jo[ok], atol=5e-3)

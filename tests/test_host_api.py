@@ -133,3 +133,18 @@ def test_tree_module_short_runs_on_oracle_backend(golden):
                         mt.result_trajectory_v[1:], mt.result_trajectory_beta[1:]], dtype=float)
         np.testing.assert_allclose(got, np.array(c["log"]), rtol=0, atol=1e-9)
         assert (mt.p - 1, mt.m, mt.recursive, mt.steps_for_slowing) == (c["ticks"], c["m"], c["recursive"], c["steps_for_slowing"])
+
+
+def test_tree_module_actual_mode_on_oracle_backend(golden):
+    """math_mpc(..., True): actuator noise (numpy.random, seeded) + all four operator events, against
+    the reference's own seeded runs -- pins rows f3 of SURVEY 8f (host logic) to the reference."""
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    c = golden("held_actual")["cases"][0]
+    mt._backend = OracleBackend()
+    np.random.seed(c["seed"])
+    mt.math_mpc([0, 0, 0, 0, 0], [2, 3], True)
+    for key, ref in c["log"].items():
+        got = np.array(getattr(mt, key), dtype=float)
+        assert got.shape == (len(ref),), key
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9, err_msg=key)
+    assert (mt.p, mt.m, mt.recursive) == (c["p"], c["m"], c["recursive"])
