@@ -154,30 +154,21 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     return kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0) + (near ? dp_rem : 0.0);
 }
 
-// float64 cost of leaf j by the reference's own formula and operation order
-// (iteration_of_predict math_model.py:110-114, control_criterion :82-86 / tree :82-87).
-// Optionally returns the poses after each step.
-__device__ __noinline__ double exact_cost(const LaunchArgs &a, const SolveParams &P, long long j,
-                                          double *traj /* [H][3] or null */, int *first_c) {
-    const bool slow = (P.flags & kFlagSlow) != 0;
-    const double4 *tab = slow ? a.g.tab64_slow : a.g.tab64;
-    const double *vt = slow ? a.g.vtab_slow : a.g.vtab;
-    double x = P.xs, y = P.ys, phi = P.phi0;
-    unsigned long long rem = (unsigned long long)j;
-    for (int k = 0; k < a.H; ++k) {
-        unsigned long long c;
-        if (a.mode == 1) c = (unsigned long long)j;
-        else { c = a.fd[k].div(rem); rem -= c * a.fd[k].d; }
-        if (k == 0 && first_c) *first_c = (int)c;
-        double dphi = __ldg(&tab[c].w);
-        double v = __ldg(&vt[c]);
-        phi = __dadd_rn(phi, dphi);
-        double sn, cs;
-        sincos(phi, &sn, &cs);
-        x = __dadd_rn(x, __dmul_rn(__dmul_rn(v, cs), a.g.dt));
-        y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, sn), a.g.dt));
-        if (traj) { traj[3 * k] = x; traj[3 * k + 1] = y; traj[3 * k + 2] = phi; }
-    }
+// ---- float64 evaluation by the reference's own formula and operation order
+// (iteration_of_predict math_model.py:110-114, control_criterion :82-86 / tree :82-87)
+__device__ __forceinline__ void exact_step(const LaunchArgs &a, const double4 *tab, const double *vt,
+                                           unsigned long long c, double &x, double &y, double &phi) {
+    const double dphi = __ldg(&tab[c].w);
+    const double v = __ldg(&vt[c]);
+    phi = __dadd_rn(phi, dphi);
+    double sn, cs;
+    sincos(phi, &sn, &cs);
+    x = __dadd_rn(x, __dmul_rn(__dmul_rn(v, cs), a.g.dt));
+    y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, sn), a.g.dt));
+}
+
+__device__ __forceinline__ double exact_terminal(const LaunchArgs &a, const SolveParams &P, double x, double y,
+                                                 double phi) {
     double dx = P.xt - x, dy = P.yt - y;
     double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
     double dl;
@@ -191,6 +182,44 @@ __device__ __noinline__ double exact_cost(const LaunchArgs &a, const SolveParams
                          __dmul_rn(100.0, dl2));
     }
     return __dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10000.0, dl2));
+}
+
+// cost of leaf j (whole walk); optionally returns the poses after each step and the first control
+__device__ __noinline__ double exact_cost(const LaunchArgs &a, const SolveParams &P, long long j,
+                                          double *traj /* [H][3] or null */, int *first_c) {
+    const bool slow = (P.flags & kFlagSlow) != 0;
+    const double4 *tab = slow ? a.g.tab64_slow : a.g.tab64;
+    const double *vt = slow ? a.g.vtab_slow : a.g.vtab;
+    double x = P.xs, y = P.ys, phi = P.phi0;
+    unsigned long long rem = (unsigned long long)j;
+    for (int k = 0; k < a.H; ++k) {
+        unsigned long long c;
+        if (a.mode == 1) c = (unsigned long long)j;
+        else { c = a.fd[k].div(rem); rem -= c * a.fd[k].d; }
+        if (k == 0 && first_c) *first_c = (int)c;
+        exact_step(a, tab, vt, c, x, y, phi);
+        if (traj) { traj[3 * k] = x; traj[3 * k + 1] = y; traj[3 * k + 2] = phi; }
+    }
+    return exact_terminal(a, P, x, y, phi);
+}
+
+// pose of depth-(H-1) node p (FULL): the shared prefix of all its children, walked once per thread
+__device__ __noinline__ void exact_prefix(const LaunchArgs &a, const SolveParams &P, unsigned long long p,
+                                          double &x, double &y, double &phi) {
+    x = P.xs; y = P.ys; phi = P.phi0;
+    unsigned long long rem = p;
+    for (int k = 0; k + 1 < a.H; ++k) {
+        unsigned long long c = a.fd[k + 1].div(rem);
+        rem -= c * a.fd[k + 1].d;
+        exact_step(a, a.g.tab64, a.g.vtab, c, x, y, phi);
+    }
+}
+
+// cost of child c of a node whose exact pose is known (same arithmetic as exact_cost's last step)
+__device__ __noinline__ double exact_child_cost(const LaunchArgs &a, const SolveParams &P, double x, double y,
+                                                double phi, unsigned c) {
+    exact_step(a, a.g.tab64, a.g.vtab, c, x, y, phi);
+    return exact_terminal(a, P, x, y, phi);
 }
 
 // candidate found by the refinement filter: evaluate and fold into the thread's running best
@@ -342,6 +371,8 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
             double base = 0.0;
             if (active) base = parent_setup(a, P, p, pr, near, unmoved);
             const bool special = active && origin_case && unmoved;
+            double ex = 0.0, ey = 0.0, ephi = 0.0;
+            bool have_pose = false;
             float best = INFINITY;
             const float thr = PASS == 2 ? __double2float_ru(tau - base) : 0.f;
             const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
@@ -363,9 +394,19 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
                         float L = near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
                                        : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
                         if (special && t.z == 0.f) L = Lspecial;
-                        if (L <= thr)
-                            take_candidate(a, P, (long long)(p * (unsigned long long)S + c0 + c),
-                                           base + (double)L, bJ, bj);
+                        if (L <= thr) {
+                            // in-window leaf: float64 re-evaluation; the node's exact pose is walked once
+                            const long long j = (long long)(p * (unsigned long long)S + c0 + c);
+                            atomicAdd(a.counters + 1, 1ULL);
+                            double J;
+                            if (a.refine) {
+                                if (!have_pose) { exact_prefix(a, P, p, ex, ey, ephi); have_pose = true; }
+                                J = exact_child_cost(a, P, ex, ey, ephi, (unsigned)(c0 + c));
+                            } else {
+                                J = P.Kbase + (base + (double)L);
+                            }
+                            lex_min(bJ, bj, J, j);
+                        }
                     }
                 }
             }
@@ -379,17 +420,21 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
 // ------------------------------------------------------------------------------------ leafwalk
 // One thread per leaf: decode the control sequence, walk H steps in registers in the start frame
 // (heading relative to the start heading, so sin.approx/cos.approx see |psi| <~ 1), score.
-template <bool HEAD>
+// KIND: 0 = FULL with 64-bit leaf indices, 1 = FULL with every index < 2^32, 2 = HELD (control j held).
+// SMEM: ctl points into shared memory (FULL trees whose {dphi, s} table fits).
+template <bool HEAD, int KIND, bool SMEM = false>
 __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveParams &P, const ParentRegs &pr,
                                                const float2 *__restrict__ ctl, unsigned long long j,
                                                float &xi, float &eta, float &psi) {
     xi = 0.f; eta = 0.f; psi = 0.f;
     unsigned long long rem = j;
+    unsigned rem32 = (unsigned)j;
     for (int k = 0; k < a.H; ++k) {
-        unsigned long long c;
-        if (a.mode == 1) c = j;
-        else { c = a.fd[k].div(rem); rem -= c * a.fd[k].d; }
-        float2 t = __ldg(ctl + c);
+        unsigned c;
+        if (KIND == 2) c = (unsigned)j;
+        else if (KIND == 1) { c = a.fd32[k].div(rem32); rem32 -= c * a.fd32[k].d; }
+        else { unsigned long long q = a.fd[k].div(rem); rem -= q * a.fd[k].d; c = (unsigned)q; }
+        float2 t = SMEM ? ctl[c] : __ldg(ctl + c);
         psi += t.x;
         float sn, cs;
         __sincosf(psi, &sn, &cs);
@@ -405,11 +450,17 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
     return L;
 }
 
-template <int PASS, bool HEAD>
+template <int PASS, bool HEAD, int KIND>
 __global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) {
+    extern __shared__ float2 s_ctl[];        // FULL trees: the {dphi, s} table, when it fits (a.lw_smem)
     __shared__ double s_J[kThreads / 32];
     __shared__ long long s_j[kThreads / 32];
     const int tid = threadIdx.x;
+    const bool staged = KIND != 2 && a.lw_smem;
+    if (staged) {
+        for (int i = tid; i < a.g.S; i += kThreads) s_ctl[i] = __ldg(a.g.ctl32 + i);
+        __syncthreads();
+    }
     const unsigned long long nwork =
         PASS == 1 ? a.total_segs : (unsigned long long)(*a.work_count) * a.tps;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -418,18 +469,25 @@ __global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) 
         const SolveParams &P = a.sp[n];
         ParentRegs pr;
         const double base = start_as_parent(P, pr);
-        const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
+        const bool smem = staged && !(P.flags & kFlagSlow);
+        const float2 *ctl = smem ? s_ctl : ((P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32);
         const float thr = PASS == 2 ? __double2float_ru(a.tau[n] - base) : 0.f;
         if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
         float best = INFINITY;
         double bJ = INFINITY; long long bj = -1;
         for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
-            const unsigned long long j = a.u_begin + tile * kThreads + tid;
-            if (j >= a.u_end) continue;
-            float xi, eta, psi;
-            const float L = leafwalk_eval<HEAD>(a, P, pr, ctl, j, xi, eta, psi);
-            if (PASS == 1) best = fminf(best, L);
-            else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
+            const unsigned long long j0 = a.u_begin + tile * (unsigned long long)(kThreads * kLeafPerThread) + tid;
+            // kLeafPerThread leaves per thread, strided by the CTA width (coalesced table reads)
+#pragma unroll 4
+            for (int k = 0; k < kLeafPerThread; ++k) {
+                const unsigned long long j = j0 + (unsigned)k * kThreads;
+                if (j >= a.u_end) break;
+                float xi, eta, psi;
+                const float L = smem ? leafwalk_eval<HEAD, KIND, true>(a, P, pr, ctl, j, xi, eta, psi)
+                                     : leafwalk_eval<HEAD, KIND, false>(a, P, pr, ctl, j, xi, eta, psi);
+                if (PASS == 1) best = fminf(best, L);
+                else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
+            }
         }
         if (PASS == 1) publish_segmin(a, seg, base + (double)best);
         else publish_best(a, n, bJ, bj, s_J, s_j);
@@ -449,7 +507,8 @@ __global__ void __launch_bounds__(kThreads) leafwalk_dump_kernel(const LaunchArg
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < a.dump_count;
          i += (unsigned long long)gridDim.x * kThreads) {
         float xi, eta, psi;
-        const float L = leafwalk_eval<HEAD>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi);
+        const float L = a.mode == 1 ? leafwalk_eval<HEAD, 2>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi)
+                                    : leafwalk_eval<HEAD, 0>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi);
         a.dump[i] = make_float4((float)P.xs + (c0 * xi - s0 * eta), (float)P.ys + (s0 * xi + c0 * eta),
                                 (float)P.phi0 + psi, L);
         jrel[i] = base + (double)L;
@@ -633,11 +692,14 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
         return head ? launch_persistent(prefix_kernel<2, true>, a, pass, sm, sms, st)
                     : launch_persistent(prefix_kernel<2, false>, a, pass, sm, sms, st);
     }
-    if (pass == 1)
-        return head ? launch_persistent(leafwalk_kernel<1, true>, a, pass, 0, sms, st)
-                    : launch_persistent(leafwalk_kernel<1, false>, a, pass, 0, sms, st);
-    return head ? launch_persistent(leafwalk_kernel<2, true>, a, pass, 0, sms, st)
-                : launch_persistent(leafwalk_kernel<2, false>, a, pass, 0, sms, st);
+    const int kind = a.mode == 1 ? 2 : (a.idx32 ? 1 : 0);
+    const size_t lw_sm = (a.mode != 1 && a.lw_smem) ? sizeof(float2) * (size_t)a.g.S : 0;
+#define MPCB_LW(P_, H_, K_) launch_persistent(leafwalk_kernel<P_, H_, K_>, a, pass, lw_sm, sms, st)
+#define MPCB_LW_KIND(P_, H_) (kind == 2 ? MPCB_LW(P_, H_, 2) : kind == 1 ? MPCB_LW(P_, H_, 1) : MPCB_LW(P_, H_, 0))
+    if (pass == 1) return head ? MPCB_LW_KIND(1, true) : MPCB_LW_KIND(1, false);
+    return head ? MPCB_LW_KIND(2, true) : MPCB_LW_KIND(2, false);
+#undef MPCB_LW_KIND
+#undef MPCB_LW
 }
 
 cudaError_t launch_reduce_compact(cudaStream_t st, const LaunchArgs &a, double *tau, unsigned *worklist,
