@@ -95,8 +95,8 @@ def test_device_closed_loop_batch_equals_per_tick_host_loop():
 def test_actual_mode_matches_reference_seeded_runs(golden):
     mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
     for c in golden("held_actual")["cases"]:
-        mt.reset_state()
         mt.x_0, mt.y_0, mt.phi_0 = 0, 0, 0
+        mt.reset_state()
         np.random.seed(c["seed"])
         mt.math_mpc([0, 0, 0, 0, 0], [2, 3], True)
         for key, ref in c["log"].items():
