@@ -188,7 +188,7 @@ def run_reference(args):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(wl, seconds_target=6.0)
+        r = cpu_sample(wl, seconds_target=float(os.environ.get("MPCB_CPU_SAMPLE_SECONDS", "6.0")))
         if i >= args.warmup:
             vals.append(r)
     v = statistics.mean(x["value"] for x in vals)
