@@ -192,3 +192,44 @@ def test_degenerate_inputs_do_not_select_a_leaf(solver):
         solver.set_grid([], B, L, DT, VMIN)
     with pytest.raises(nat.MpcbError):
         solver.solve(nat.MODE_FULL, nat.COST_MM, 3, [0.0, 0.0, 0.0], (1.0, 1.0), (0.0, 0.0))  # grid was dropped
+
+
+def test_prefix_multi_chunk_table_and_reference_default_grid(solver):
+    """S > 1024 makes the prefix kernel stream the leaf table through shared memory in chunks.
+    (a) 30x50 grid, H=2 and 3 restricted to a few first controls; (b) the reference's own default
+    201x121 grid (S=24,321, math_model.py:23-30) at H=2: 5.9e8 leaves, the tree the reference cannot allocate."""
+    V, B = np.linspace(0.0, 1.0, 30), np.linspace(-1.0, 1.0, 50)
+    solver.set_grid(V, B, L, DT, VMIN)
+    solver.set_option("algo", nat.ALGO_PREFIX)
+    try:
+        sc = C.random_scenarios(3, 21)
+        res = solver.solve(nat.MODE_FULL, nat.COST_MM, 2, sc[:, :3], sc[:, 3:5], sc[:, :2])
+        for i, s in enumerate(sc):
+            _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, 2, C.COST_MM), 2)
+        s = sc[0]
+        r = solver.solve(nat.MODE_FULL, nat.COST_TREE, 3, s[:3], s[3:5], s[:2], i0_range=(1490, 1500))
+        o = K.solve_full(s[:3], s[3:], s[:2], V, B, 3, C.COST_TREE, i0_range=(1490, 1500))
+        assert r["index"][0] == o["index"] and r["cost"][0] == pytest.approx(o["cost"], rel=1e-12)
+        Vd, Bd = C.grid_full_default()
+        solver.set_grid(Vd, Bd, L, DT, VMIN)
+        s = np.array([0.0, 0.0, 0.0, 1.0, 5.0])          # config.py start and target; the start IS the line origin
+        r = solver.solve(nat.MODE_FULL, nat.COST_MM, 2, s[:3], s[3:5], s[:2])
+        assert solver.stats()["leaves_per_solve"] == 24321 ** 2
+        _check(r, 0, K.solve_full(s[:3], s[3:], s[:2], Vd, Bd, 2, C.COST_MM), 2)
+    finally:
+        solver.set_option("algo", nat.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+def test_long_horizons(solver, algo):
+    """H = 6 and 8 (the reference hard-codes 3): index decoding over many digits, 64-bit paths."""
+    solver.set_option("algo", algo)
+    try:
+        for H, V, B in ((6, [0.2, 1.0], np.linspace(-0.9, 0.9, 4)), (8, [0.5, 1.0], [-0.8, 0.0, 0.8])):
+            solver.set_grid(V, B, L, DT, VMIN)
+            sc = C.random_scenarios(4, 30 + H)
+            res = solver.solve(nat.MODE_FULL, nat.COST_TREE, H, sc[:, :3], sc[:, 3:5], sc[:, :2])
+            for i, s in enumerate(sc):
+                _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, C.COST_TREE), H)
+    finally:
+        solver.set_option("algo", nat.ALGO_AUTO)
