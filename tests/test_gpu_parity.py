@@ -233,3 +233,62 @@ def test_long_horizons(solver, algo):
                 _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, C.COST_TREE), H)
     finally:
         solver.set_option("algo", nat.ALGO_AUTO)
+
+
+def test_config0_default_full_tree_subtrees(solver):
+    """BASELINE configs[0]: run_math_model.py's default scenario -- start (0,0,0), target (1,5), H=3 on the
+    201x121 grid: 1.44e13 leaves (the reference's np.empty([S**3, 3]) is a 345 TB allocation).  Here: three
+    first-control subtrees (5.9e8 leaves each) against the C oracle; the whole tree is timed in profiles/."""
+    Vd, Bd = C.grid_full_default()
+    solver.set_grid(Vd, Bd, L, DT, VMIN)
+    s = np.array([0.0, 0.0, 0.0, 1.0, 5.0])
+    for i0 in (0, 12160, 24320):
+        r = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, s[:3], s[3:5], s[:2], i0_range=(i0, i0 + 1))
+        o = K.solve_full(s[:3], s[3:], s[:2], Vd, Bd, 3, C.COST_MM, i0_range=(i0, i0 + 1))
+        assert r["index"][0] == o["index"], (i0, r["index"][0], o["index"])
+        assert r["cost"][0] == pytest.approx(o["cost"], rel=1e-12)
+        np.testing.assert_allclose(r["traj"][0], o["traj"], rtol=0, atol=1e-12)
+
+
+def _eps_model(s, origin, H, cost, prefix, smax, dphimax):
+    """Python mirror of the error window prep_kernel computes (tol/2)."""
+    xs, ys, p0, xt, yt = s
+    wl, wh = (10.0, math.sqrt(10.0)) if cost == C.COST_MM else (100.0, 0.0)
+    A, Bc, Cc = yt - origin[1], xt - origin[0], xt * origin[1] - yt * origin[0]
+    norm = math.hypot(A, Bc)
+    e0 = wl * (A * xs - Bc * ys + Cc) / norm
+    hp0 = wh * (C.heading_reference(xt, yt) - p0)
+    Rtot = H * smax
+    Rl = smax if prefix else Rtot
+    Gl = wh * (dphimax if prefix else H * dphimax)
+    E, Hh, Q = abs(e0) + wl * Rtot, abs(hp0) + wh * H * dphimax, wl * Rl
+    M = 1e4 * Rl * 16 + 4 * Q * (2 * E + Q) + 4 * Gl * (Gl + 2 * Hh)
+    if not prefix:
+        M += 1e4 * Rtot * 8
+    return M * 2.0 ** -23
+
+
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_fp32_stage_error_stays_inside_the_refinement_window(solver, algo, cost):
+    """Every leaf of many small trees (far / near the target / far off the tracked line): the fp32 value the
+    kernels compare lies within the per-solve window half-width eps that the refinement pass assumes."""
+    V, B = [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 9)
+    solver.set_grid(V, B, L, DT, VMIN)
+    vv, bb, dphi = C.control_tables(V, B, L, DT)
+    smax, dphimax = float(np.max(vv) * DT), float(np.max(np.abs(dphi)))
+    H = 3
+    sc = C.random_scenarios(10, 77)
+    cases = [(s, s[:2]) for s in sc]
+    for s in sc[:5]:
+        n = s.copy(); n[3], n[4] = n[0] + 0.06, n[1] + 0.04           # NEAR regime
+        cases.append((n, n[:2]))
+        cases.append((s, s[:2] + np.array([3.0, -2.0])))              # robot metres away from the tracked line
+    worst_ratio = 0.0
+    for s, origin in cases:
+        _, J = solver.dump_leaves(nat.MODE_FULL, COSTS[cost], H, s[:3], s[3:5], origin, algo=algo)
+        Jo = C.full_leaf_costs(s[:3], s[3:5], origin, V, B, H, cost)
+        ok = Jo < 1e7
+        eps = _eps_model(s, origin, H, cost, algo == nat.ALGO_PREFIX, smax, dphimax)
+        worst_ratio = max(worst_ratio, float(np.abs(J - Jo)[ok].max() / eps))
+    assert worst_ratio < 1.0, worst_ratio
