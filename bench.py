@@ -229,6 +229,8 @@ def run_gpu(args):
     solver = nat.Solver(local)
     solver.set_grid(wl["V"], wl["B"], C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
     solver.set_option("algo", {"auto": nat.ALGO_AUTO, "prefix": nat.ALGO_PREFIX, "leafwalk": nat.ALGO_LEAFWALK}[args.algo])
+    # the headline evaluates EVERY leaf (as the reference does); the exact branch-and-bound is reported separately
+    solver.set_option("prune", 0)
 
     # each rank owns its own robots (contiguous ranges of the global batch): no data-path collective
     scen = C.random_scenarios(n * world, wl["seed"])[rank * n:(rank + 1) * n]
@@ -314,6 +316,33 @@ def run_gpu(args):
         if ok != chk:
             raise SystemExit("PARITY FAILURE in bench: " + parity)
 
+    # ---------------- same step with the exact branch-and-bound on (identical results, fewer leaves evaluated)
+    pruned = None
+    if args.algo != "leafwalk":
+        solver.set_option("prune", 1)
+        with torch.cuda.stream(ext):
+            step_device()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            p0.record()
+            for _ in range(args.steps):
+                step_device()
+            p1.record()
+        barrier()
+        pst = solver.stats()
+        same = bool(torch.equal(oi.cpu(), torch.from_numpy(out_np["index"])))
+        tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        parents = pst["units"] * n
+        pruned = dict(ms_per_step=float(tp[0]) / args.steps, solves_per_s=n * world * args.steps / (float(tp[0]) * 1e-3),
+                      evaluated_fraction=1.0 - pst["pruned_units"] / max(parents, 1), same_leaves_as_unpruned=same,
+                      note="option prune=1: depth-(H-1) nodes whose children provably cannot reach the refinement "
+                           "window are skipped; `value` above is measured with prune=0 (every leaf evaluated)")
+        if not same:
+            raise SystemExit("PARITY FAILURE in bench: pruned and unpruned solves disagree")
+        solver.set_option("prune", 0)
     solver.set_option("algo", nat.ALGO_AUTO)
     held = held_metrics(solver, nat, C, local) if rank == 0 and args.algo == "auto" else None
     if rank == 0:
@@ -348,7 +377,7 @@ def run_gpu(args):
             e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      solves_per_s=n * world * args.steps / float(te[0])),
             gpu_launches=stats["kernel_launches"] * args.steps,
-            clocks=clocks, parity=parity, held=held,
+            clocks=clocks, parity=parity, held=held, pruned=pruned,
             refine=dict(segments=stats["refine_segments"], candidates=stats["refine_candidates"]),
         )
         if world == 1 and not args.no_cpu:

@@ -19,6 +19,7 @@ cudaError_t launch_prep(cudaStream_t, long long, const double *, const double *,
                         const uint8_t *, int, int, int, double, double, double, SolveParams *);
 cudaError_t launch_pass(cudaStream_t, const LaunchArgs &, int pass, bool prefix, int sms);
 cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, unsigned *, unsigned *, int sms);
+cudaError_t launch_probe(cudaStream_t, const LaunchArgs &, int sms);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
@@ -83,9 +84,10 @@ struct mpcb_handle_s {
     double tol_scale = 1.0;
     int algo = MPCB_ALGO_AUTO;
     int refine = 1;
-    int small_path = 1;   // host-API HELD solves with few candidates take the one-launch float64 path
+    int small_path = 1;
+    int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
-    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock;
+    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub;
     DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
     DevBuf loop_log, loop_ticks, loop_status, small_in, small_out;
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
@@ -128,6 +130,7 @@ bool pow_checked(unsigned long long S, int H, unsigned long long &out) {
 struct Plan {
     bool prefix;
     unsigned long long u_begin, u_end, leaves_per_solve;
+    long long i0_begin = 0, i0_end = 0;
 };
 
 int make_plan(mpcb_handle *h, int mode, int H, long long N, long long i0_begin, long long i0_end, int algo_req,
@@ -160,6 +163,7 @@ int make_plan(mpcb_handle *h, int mode, int H, long long N, long long i0_begin, 
         pl.u_end = (unsigned long long)i0_end * sub;
     }
     pl.leaves_per_solve = (unsigned long long)(i0_end - i0_begin) * sub;
+    pl.i0_begin = i0_begin; pl.i0_end = i0_end;
     return MPCB_OK;
 }
 
@@ -176,6 +180,7 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
         if (mode == MPCB_MODE_FULL) pw *= S;
     }
     a.u_begin = pl.u_begin; a.u_end = pl.u_end;
+    a.i0_begin = (int)pl.i0_begin; a.i0_end = (int)pl.i0_end;
     a.tile_units = pl.prefix ? kThreads : kThreads * kLeafPerThread;
     a.lw_smem = (!pl.prefix && mode == MPCB_MODE_FULL && h->g.S <= 4096) ? 1 : 0;
 }
@@ -293,7 +298,7 @@ int mpcb_destroy(mpcb_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
-                      &h->lock, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
+                      &h->lock, &h->ub, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
                       &h->loop_status, &h->small_in, &h->small_out})
         b->release();
@@ -320,6 +325,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "algo")) h->algo = (int)value;
     else if (!strcmp(name, "refine")) h->refine = value != 0.0;
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
+    else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else return fail(h, MPCB_ERR_INVALID, "unknown option '%s'", name);
     return MPCB_OK;
 }
@@ -383,7 +389,8 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     CK(h->bestJ.ensure(sizeof(double) * N));
     CK(h->bestIdx.ensure(sizeof(long long) * N));
     CK(h->lock.ensure(sizeof(int) * N));
-    // misc: [0..7] work_count (u32) | [16..31] counters (2 x u64)
+    CK(h->ub.ensure(sizeof(unsigned long long) * N));
+    // misc: [0..7] work_count (u32) | [16..39] counters (3 x u64)
     unsigned *work_count = h->misc.as<unsigned>();
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
     CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
@@ -398,10 +405,15 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     a.lock = h->lock.as<int>();
     a.counters = counters;
     a.tau = h->tau.as<double>();
+    a.ub = h->ub.as<unsigned long long>();
+    a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
 
     int launches = 0;
     CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, pl.prefix ? 1 : 0,
                    h->g.smax, h->g.dphimax, h->tol_scale, h->sp.as<SolveParams>())); ++launches;
+    if (a.prune) {
+        CK(launch_probe(h->stream, a, h->sms)); ++launches;
+    }
     if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
     }
@@ -425,11 +437,12 @@ int mpcb_get_stats(mpcb_handle *h, mpcb_stats *out) {
     if (!h || !out) return MPCB_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (h->stats.refine_segments < 0 && h->misc.p) {
-        unsigned long long c[2] = {0, 0};
+        unsigned long long c[3] = {0, 0, 0};
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaMemcpy(c, h->misc.as<char>() + 16, sizeof c, cudaMemcpyDeviceToHost));
         h->stats.refine_segments = (int64_t)c[0];
         h->stats.refine_candidates = (int64_t)c[1];
+        h->stats.pruned_units = (int64_t)c[2];
     }
     *out = h->stats;
     return MPCB_OK;

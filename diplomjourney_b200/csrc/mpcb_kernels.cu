@@ -121,8 +121,15 @@ __device__ __forceinline__ double start_as_parent(const SolveParams &P, ParentRe
 
 // float64 walk of the prefix (i_0 .. i_{H-2}) of depth-(H-1) node p in the start frame, then the
 // node's frame quantities.  Returns base_p (float64) and whether the node has not moved at all.
+// min over |q| <= Q of q^2 + e q  (the line / heading offset terms of leaf_val are of this form)
+__device__ __forceinline__ double quad_min(double e, double Q) {
+    const double ae = fabs(e);
+    return ae <= 2.0 * Q ? -0.25 * e * e : Q * (Q - ae);
+}
+
 __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
-                                               unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved) {
+                                               unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved,
+                                               double *lower_bound = nullptr) {
     double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
     unsigned long long rem = p;
     const int D = a.H - 1;
@@ -151,7 +158,12 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     pr.e2 = (float)(2.0 * ep); pr.h2 = (float)(2.0 * hp);
     near = !(Dp >= 4.0 * a.g.smax);
     // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
-    return kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0) + (near ? dp_rem : 0.0);
+    const double base0 = kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
+    // no child can do better than: one step straight at the target (d >= Dp - s_max, triangle inequality)
+    // plus the most favourable line and heading offsets  (|q| <= wl s_max, |g| <= wh dphi_max)
+    if (lower_bound)
+        *lower_bound = base0 - kWd * a.g.smax + quad_min(2.0 * ep, P.wl * a.g.smax) + quad_min(-2.0 * hp, P.wh * a.g.dphimax);
+    return base0 + (near ? dp_rem : 0.0);
 }
 
 // ---- float64 evaluation by the reference's own formula and operation order
@@ -365,11 +377,24 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
         double bJ = INFINITY; long long bj = -1;
         for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
             const unsigned long long p = a.u_begin + tile * kThreads + tid;
-            const bool active = p < a.u_end;
+            const bool in_range = p < a.u_end;
             ParentRegs pr = {};
             bool near = false, unmoved = false;
-            double base = 0.0;
-            if (active) base = parent_setup(a, P, p, pr, near, unmoved);
+            double base = 0.0, lb = -INFINITY;
+            bool active = in_range;
+            if (active) base = parent_setup(a, P, p, pr, near, unmoved, &lb);
+            if (a.prune) {
+                // exact branch-and-bound: a node none of whose children can come within the refinement window of
+                // the best leaf known so far is skipped (pass 1: running upper bound; pass 2: the final window edge)
+                const double bound = PASS == 1 ? ordered_value(*(volatile unsigned long long *)(a.ub + n)) + 2.0 * P.tol
+                                               : tau + P.tol;
+                const bool cut = active && lb > bound;
+                if (PASS == 1) {
+                    const unsigned m = __ballot_sync(0xffffffffu, cut);
+                    if ((tid & 31) == 0 && m) atomicAdd(a.counters + 2, (unsigned long long)__popc(m));
+                }
+                active = active && !cut;
+            }
             const bool special = active && origin_case && unmoved;
             double ex = 0.0, ey = 0.0, ephi = 0.0;
             bool have_pose = false;
@@ -411,6 +436,11 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
                 }
             }
             if (PASS == 1 && active) segbest = fmin(segbest, base + (double)best);
+            if (PASS == 1 && a.prune) {
+                // tighten the solve's upper bound: this tile's best fp32 value + its error bound is >= a true leaf cost
+                const double v = warp_min(active ? base + (double)best : INFINITY);
+                if ((tid & 31) == 0 && v < INFINITY) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol));
+            }
         }
         if (PASS == 1) publish_segmin(a, seg, segbest);
         else publish_best(a, n, bJ, bj, s_J, s_j);
@@ -587,6 +617,30 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     out[n] = P;
 }
 
+// Pruning probe (FULL): the S "held" sequences (c, c, ..., c) are leaves of the FULL tree, so the best of them,
+// evaluated exactly, is an upper bound on the minimal cost: it seeds the branch-and-bound before pass 1.
+__global__ void __launch_bounds__(kThreads) probe_kernel(const LaunchArgs a) {
+    __shared__ double s_J[kThreads / 32];
+    for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
+        const SolveParams &P = a.sp[n];
+        double best = INFINITY;
+        // only sequences whose first control lies in this launch's share of the tree are leaves of it
+        for (int c = a.i0_begin + threadIdx.x; c < a.i0_end; c += kThreads) {
+            double x = P.xs, y = P.ys, phi = P.phi0;
+            for (int k = 0; k < a.H; ++k) exact_step(a, a.g.tab64, a.g.vtab, c, x, y, phi);
+            best = fmin(best, exact_terminal(a, P, x, y, phi));
+        }
+        best = warp_min(best);
+        if ((threadIdx.x & 31) == 0) s_J[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < kThreads / 32; ++i) best = fmin(best, s_J[i]);
+            a.ub[n] = best < INFINITY ? ordered_key(best - P.Kbase) : ~0ULL;
+        }
+        __syncthreads();
+    }
+}
+
 // Per solve: minimum of its segment minima -> window edge tau; segments inside the window -> work list.
 __global__ void __launch_bounds__(kThreads) reduce_compact_kernel(const LaunchArgs a, double *tau,
                                                                   unsigned *worklist, unsigned *work_count) {
@@ -700,6 +754,11 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
     return head ? MPCB_LW_KIND(2, true) : MPCB_LW_KIND(2, false);
 #undef MPCB_LW_KIND
 #undef MPCB_LW
+}
+
+cudaError_t launch_probe(cudaStream_t st, const LaunchArgs &a, int sms) {
+    probe_kernel<<<grid_for((unsigned long long)a.N, sms, 8), kThreads, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_compact(cudaStream_t st, const LaunchArgs &a, double *tau, unsigned *worklist,

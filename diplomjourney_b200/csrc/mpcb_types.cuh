@@ -104,7 +104,10 @@ struct LaunchArgs {
     double *bestJ;                         // [N] exact cost of the best candidate so far
     long long *bestIdx;                    // [N]
     int *lock;                             // [N]
-    unsigned long long *counters;          // [0] refine segments, [1] candidates
+    unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes
+    unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
+    int prune;
+    int i0_begin, i0_end;                   // first-control range of this launch (probe)
     const double *tau;                     // [N] J_rel window upper edge
     // dump
     float4 *dump;                          // {x, y, phi, J_rel} per leaf

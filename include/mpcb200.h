@@ -87,7 +87,9 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
 
 /* Options: "tol_scale" (candidate-window multiplier, default 1), "algo" (MPCB_ALGO_*),
  * "refine" (1 = float64 re-evaluation of near-minimal leaves, default; 0 = fp32 winner),
- * "small_path" (1 = host-API HELD solves with <= 4096 candidates run as one float64 launch, default). */
+ * "small_path" (1 = host-API HELD solves with <= 4096 candidates run as one float64 launch, default),
+ * "prune" (1 = exact branch-and-bound in the prefix kernel: depth-(H-1) nodes whose children provably cannot
+ * reach the refinement window of the best leaf are skipped -- identical results; default 1, 0 = evaluate every leaf). */
 MPCB_API int mpcb_set_option(mpcb_handle *h, const char *name, double value);
 
 /* Batch of N independent MPC solves sharing the grid.  Replaces N calls of
@@ -133,6 +135,7 @@ typedef struct {
     int64_t segments;         /* pass-1 partial minima */
     int64_t refine_segments;  /* segments re-run by the float64 refinement pass */
     int64_t refine_candidates;/* leaves re-evaluated in float64 */
+    int64_t pruned_units;     /* depth-(H-1) nodes (x N solves) skipped by the exact branch-and-bound */
     int32_t algo;             /* MPCB_ALGO_* actually used */
     int32_t kernel_launches;  /* kernels enqueued by the last solve */
 } mpcb_stats;
