@@ -18,6 +18,7 @@ MODE_FULL, MODE_HELD = 0, 1
 COST_MM, COST_TREE = 0, 1
 ALGO_AUTO, ALGO_LEAFWALK, ALGO_PREFIX = 0, 1, 2
 FLAG_SLOW = 1
+FLAG_SKIP = 2
 MAX_H = 8
 
 _ERR = {-1: "invalid argument", -2: "CUDA error", -3: "no grid set", -4: "empty control grid",
@@ -94,6 +95,7 @@ def load():
     loop = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mpcb_held_closed_loop_host.argtypes = loop
     lib.mpcb_held_closed_loop_device.argtypes = loop
+    lib.mpcb_full_closed_loop_host.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_double, C.c_int, vp, vp, vp]
     lib.mpcb_allreduce_min.argtypes = [vp, vp, vp, vp]
     lib.mpcb_nccl_unique_id.argtypes = [vp]
     lib.mpcb_nccl_comm_create.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
@@ -215,6 +217,22 @@ class Solver:
         status = np.empty(N, np.int32)
         self._ck(self.lib.mpcb_held_closed_loop_host(self.h, C.byref(params), N, _ptr(ini), _ptr(tg), _ptr(og), _ptr(thr),
                                                      _ptr(sl), _ptr(log), _ptr(ticks), _ptr(status)))
+        return dict(log=log, ticks=ticks, status=status)
+
+    def full_closed_loop(self, cost, H, init_state, target, origin, first_threshold=None, eps=0.001, max_ticks=256):
+        """Closed loop of the FULL-tree scripts for a batch of robots (mpcb_full_closed_loop_host): one batched
+        FULL solve per tick with the carried threshold; stops per robot on target / after two repeated
+        positions / at max_ticks. Returns dict(log[N,max_ticks,5], ticks[N], status[N])."""
+        ini = _arr(init_state, np.float64, (-1, 3))
+        N = ini.shape[0]
+        tg = _arr(np.broadcast_to(np.asarray(target, np.float64).reshape(-1, 2), (N, 2)), np.float64)
+        og = _arr(np.broadcast_to(np.asarray(origin, np.float64).reshape(-1, 2), (N, 2)), np.float64)
+        thr = None if first_threshold is None else _arr(np.broadcast_to(np.asarray(first_threshold, np.float64), (N,)), np.float64)
+        log = np.empty((N, max_ticks, 5))
+        ticks = np.empty(N, np.int32)
+        status = np.empty(N, np.int32)
+        self._ck(self.lib.mpcb_full_closed_loop_host(self.h, cost, H, N, _ptr(ini), _ptr(tg), _ptr(og), _ptr(thr),
+                                                     float(eps), int(max_ticks), _ptr(log), _ptr(ticks), _ptr(status)))
         return dict(log=log, ticks=ticks, status=status)
 
     def dump_leaves(self, mode, cost, H, state, target, origin, flags=0, algo=ALGO_LEAFWALK, leaf_begin=0, count=None):

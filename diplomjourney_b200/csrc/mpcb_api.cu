@@ -24,6 +24,7 @@ cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long lon
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
 cudaError_t launch_held_small(cudaStream_t, const SmallArgs &);
+cudaError_t launch_full_apply(cudaStream_t, const FullLoopArgs &);
 }  // namespace mpcb
 
 using namespace mpcb;
@@ -89,7 +90,7 @@ struct mpcb_handle_s {
     // scratch
     DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub;
     DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
-    DevBuf loop_log, loop_ticks, loop_status, small_in, small_out;
+    DevBuf loop_log, loop_ticks, loop_status, small_in, small_out, fl_last, fl_k, fl_have, fl_flags, fl_count;
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
     size_t pin_in_cap = 0, pin_out_cap = 0;
     mpcb_stats stats{};
@@ -300,7 +301,8 @@ int mpcb_destroy(mpcb_handle *h) {
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
                       &h->lock, &h->ub, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
-                      &h->loop_status, &h->small_in, &h->small_out})
+                      &h->loop_status, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
+                      &h->fl_count})
         b->release();
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -673,6 +675,78 @@ int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_
     CK(cudaMemcpyAsync(out_ticks, h->loop_ticks.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_status, h->loop_status.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return MPCB_OK;
+}
+
+int mpcb_full_closed_loop_host(mpcb_handle *h, int cost_kind, int H, int64_t N, const double *init_state,
+                               const double *target, const double *origin, const double *first_threshold,
+                               double eps, int max_ticks, double *out_log, int32_t *out_ticks, int32_t *out_status) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
+    if (!init_state || !target || !origin || !out_log || !out_ticks || !out_status || max_ticks < 1)
+        return fail(h, MPCB_ERR_INVALID, "full closed loop: bad arguments");
+    if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t nlog = (size_t)N * max_ticks * 5;
+    CK(h->in_state.ensure(sizeof(double) * 3 * N)); CK(h->in_target.ensure(sizeof(double) * 2 * N));
+    CK(h->in_origin.ensure(sizeof(double) * 2 * N)); CK(h->in_thr.ensure(sizeof(double) * N));
+    CK(h->out_cost.ensure(sizeof(double) * N)); CK(h->out_index.ensure(sizeof(int64_t) * N));
+    CK(h->out_traj.ensure(sizeof(double) * 3 * H * N)); CK(h->out_ctl.ensure(sizeof(double) * 2 * N));
+    CK(h->loop_log.ensure(sizeof(double) * nlog)); CK(h->loop_ticks.ensure(sizeof(int) * N));
+    CK(h->loop_status.ensure(sizeof(int) * N)); CK(h->fl_last.ensure(sizeof(double) * 5 * N));
+    CK(h->fl_k.ensure(sizeof(int) * N)); CK(h->fl_have.ensure(sizeof(int) * N));
+    CK(h->fl_flags.ensure(N)); CK(h->fl_count.ensure(sizeof(int)));
+    // robots that start on their target never enter the loop (while not is_on_target, math_model.py:239)
+    std::vector<int> status(N, -1);
+    std::vector<unsigned char> flags(N, 0);
+    std::vector<double> thr(N);
+    int running = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        const double dx = target[2 * i] - init_state[3 * i], dy = target[2 * i + 1] - init_state[3 * i + 1];
+        if (dx * dx + dy * dy <= eps) { status[i] = MPCB_LOOP_ON_TARGET; flags[i] = MPCB_FLAG_SKIP; }
+        else ++running;
+        thr[i] = first_threshold ? first_threshold[i] : INFINITY;
+    }
+    CK(cudaMemcpyAsync(h->in_state.p, init_state, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_target.p, target, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_origin.p, origin, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->in_thr.p, thr.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->loop_status.p, status.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->fl_flags.p, flags.data(), N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->fl_k.p, 0, sizeof(int) * N, st));
+    CK(cudaMemsetAsync(h->fl_have.p, 0, sizeof(int) * N, st));
+    CK(cudaMemsetAsync(h->loop_ticks.p, 0, sizeof(int) * N, st));
+    CK(cudaMemsetAsync(h->loop_log.p, 0xFF, sizeof(double) * nlog, st));     // NaN pattern for unused rows
+    CK(cudaStreamSynchronize(st));      // the staging vectors above are pageable
+    FullLoopArgs fa{};
+    fa.N = N; fa.H = H; fa.max_ticks = max_ticks; fa.eps = eps;
+    fa.target = h->in_target.as<double>();
+    fa.best_cost = h->out_cost.as<double>(); fa.best_index = h->out_index.as<long long>();
+    fa.best_traj = h->out_traj.as<double>(); fa.first_control = h->out_ctl.as<double>();
+    fa.state = h->in_state.as<double>(); fa.threshold = h->in_thr.as<double>(); fa.last_ret = h->fl_last.as<double>();
+    fa.kcount = h->fl_k.as<int>(); fa.have_ret = h->fl_have.as<int>(); fa.status = h->loop_status.as<int>();
+    fa.ticks = h->loop_ticks.as<int>(); fa.flags = h->fl_flags.as<unsigned char>();
+    fa.log = h->loop_log.as<double>(); fa.active_count = h->fl_count.as<int>();
+    int total_launches = 0;
+    for (int tick = 0; tick < max_ticks && running > 0; ++tick) {
+        CK(cudaMemsetAsync(h->fl_count.p, 0, sizeof(int), st));
+        int rc = mpcb_solve_batch_device(h, MPCB_MODE_FULL, cost_kind, H, N, h->in_state.as<double>(),
+                                         h->in_target.as<double>(), h->in_origin.as<double>(), h->in_thr.as<double>(),
+                                         h->fl_flags.as<uint8_t>(), 0, -1, h->out_cost.as<double>(),
+                                         h->out_index.as<int64_t>(), h->out_traj.as<double>(), h->out_ctl.as<double>());
+        if (rc) return rc;
+        total_launches += h->stats.kernel_launches + 1;
+        fa.tick = tick;
+        CK(launch_full_apply(st, fa));
+        CK(cudaMemcpyAsync(&running, h->fl_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaMemcpyAsync(out_log, h->loop_log.p, sizeof(double) * nlog, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_ticks, h->loop_ticks.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_status, h->loop_status.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->stats.kernel_launches = total_launches;
     return MPCB_OK;
 }
 

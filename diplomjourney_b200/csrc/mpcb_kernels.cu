@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
         decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
         const SolveParams &P = a.sp[n];
+        if (P.flags & kFlagSkip) continue;               // a robot that has already stopped (uniform per work item)
         const bool origin_case = (P.flags & kFlagStartIsOrigin) != 0;
         const double tau = PASS == 2 ? a.tau[n] : 0.0;
         if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) 
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
         decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
         const SolveParams &P = a.sp[n];
+        if (P.flags & kFlagSkip) continue;
         ParentRegs pr;
         const double base = start_as_parent(P, pr);
         const bool smem = staged && !(P.flags & kFlagSlow);
@@ -604,6 +606,7 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     P.Kbase = kWd * P.d0 + P.e0 * P.e0 + P.hp0 * P.hp0;
     P.special = 1.0e6 * P.wl * P.wl;
     int f = flags ? (flags[n] & kFlagSlow) : 0;
+    if (flags && (flags[n] & 2)) f |= kFlagSkip;          // MPCB_FLAG_SKIP
     if (P.xs == P.ox && P.ys == P.oy) f |= kFlagStartIsOrigin;
     // error model of the fp32 leaf part
     const double Rtot = H * smax;
@@ -625,6 +628,7 @@ __global__ void __launch_bounds__(kThreads) probe_kernel(const LaunchArgs a) {
     __shared__ double s_J[kThreads / 32];
     for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
         const SolveParams &P = a.sp[n];
+        if (P.flags & kFlagSkip) { if (threadIdx.x == 0) a.ub[n] = ~0ULL; continue; }
         double best = INFINITY;
         // only sequences whose first control lies in this launch's share of the tree are leaves of it
         for (int c = a.i0_begin + threadIdx.x; c < a.i0_end; c += kThreads) {

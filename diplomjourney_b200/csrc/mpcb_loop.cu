@@ -255,6 +255,49 @@ cudaError_t launch_held_small(cudaStream_t st, const SmallArgs &a) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// FULL closed loop: what the host loop of math_model.py:239-254 does between two predictive_control calls,
+// one thread per robot, after the tick's batched solve.
+__global__ void full_apply_kernel(const FullLoopArgs a) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N || a.status[n] >= 0) return;
+    double ret[5];
+    const long long idx = a.best_index[n];
+    if (idx >= 0) {                                        // a leaf beat the carried optimum (strict '<')
+        const double *tr = a.best_traj + (size_t)n * 3 * a.H;
+        ret[0] = tr[0]; ret[1] = tr[1]; ret[2] = tr[2];
+        ret[3] = a.first_control[2 * n]; ret[4] = a.first_control[2 * n + 1];
+        a.threshold[n] = a.best_cost[n];
+        a.have_ret[n] = 1;
+    } else if (!a.have_ret[n]) {                           // reference: IndexError on the placeholder trajectory
+        a.status[n] = MPCB_LOOP_NO_LEAF;
+        a.flags[n] = MPCB_FLAG_SKIP;
+        return;
+    } else {                                               // stall: the previous path is returned again
+        for (int k = 0; k < 5; ++k) ret[k] = a.last_ret[5 * n + k];
+    }
+    double *log = a.log + ((size_t)n * a.max_ticks + a.tick) * 5;
+    for (int k = 0; k < 5; ++k) { log[k] = ret[k]; a.last_ret[5 * n + k] = ret[k]; }
+    const double xprev = a.state[3 * n], yprev = a.state[3 * n + 1];
+    a.state[3 * n] = ret[0]; a.state[3 * n + 1] = ret[1]; a.state[3 * n + 2] = ret[2];
+    a.ticks[n] = a.tick + 1;
+    int k = a.kcount[n];
+    if (ret[0] == xprev && ret[1] == yprev) a.kcount[n] = ++k;
+    const double dx = a.target[2 * n] - ret[0], dy = a.target[2 * n + 1] - ret[1];
+    int status = -1;
+    if (k == 2) status = MPCB_LOOP_STALLED;
+    else if (dx * dx + dy * dy <= a.eps) status = MPCB_LOOP_ON_TARGET;
+    else if (a.tick + 1 >= a.max_ticks) status = MPCB_LOOP_MAX_TICKS;
+    if (status >= 0) { a.status[n] = status; a.flags[n] = MPCB_FLAG_SKIP; }
+    else atomicAdd(a.active_count, 1);
+}
+
+cudaError_t launch_full_apply(cudaStream_t st, const FullLoopArgs &a) {
+    const int bs = 128;
+    full_apply_kernel<<<(unsigned)((a.N + bs - 1) / bs), bs, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_held_loop(cudaStream_t st, const LoopArgs &a, int sms) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, held_loop_kernel, kLoopThreads, 0) != cudaSuccess || per_sm < 1)

@@ -82,7 +82,7 @@ struct __align__(16) SolveParams {
     int flags;                  // bit0 slow, bit1 start_is_origin, bit2 near (leafwalk regime)
     int pad;
 };
-constexpr int kFlagSlow = 1, kFlagStartIsOrigin = 2, kFlagNear = 4;
+constexpr int kFlagSlow = 1, kFlagStartIsOrigin = 2, kFlagNear = 4, kFlagSkip = 8;
 
 struct LaunchArgs {
     GridTables g;
@@ -122,6 +122,20 @@ struct LoopArgs {
     const int *slow_steps;
     double *out_log;
     int *out_ticks, *out_status;
+};
+
+// per-tick bookkeeping of the FULL closed loop (mpcb_loop.cu)
+struct FullLoopArgs {
+    long long N;
+    int H, tick, max_ticks;
+    double eps;
+    const double *target;                              // [N][2]
+    const double *best_cost; const long long *best_index; const double *best_traj, *first_control;   // this tick's solve
+    double *state, *threshold, *last_ret;              // [N][3], [N], [N][5]
+    int *kcount, *have_ret, *status, *ticks;           // [N]
+    unsigned char *flags;                              // [N] MPCB_FLAG_SKIP once a robot has stopped
+    double *log;                                       // [N][max_ticks][5]
+    int *active_count;
 };
 
 // one-launch float64 HELD solve from the raw grids (mpcb_loop.cu); all pointers are device

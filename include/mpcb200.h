@@ -67,6 +67,7 @@ typedef enum {
 
 /* per-solve flags (uint8 per solve) */
 #define MPCB_FLAG_SLOW 1 /* steps_for_slowing > 0: every velocity := max(min(V), v_min), math_model_tree.py:312-316 */
+#define MPCB_FLAG_SKIP 2 /* do not solve this entry (a robot of a batch that has already stopped): index -1, cost NaN */
 
 MPCB_API int mpcb_version(void);
 MPCB_API int mpcb_device_count(void);
@@ -181,6 +182,17 @@ MPCB_API int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params
                                  const double *init, const double *target, const double *origin,
                                  const double *first_threshold, const int32_t *slow_steps,
                                  double *out_log, int32_t *out_ticks, int32_t *out_status);
+
+/* Closed loop of the FULL-tree scripts for a batch of robots (math_model.py:234-254 / run_math_model.py:261-276):
+ * every tick solves all still-running robots in ONE batched FULL solve with the CARRIED threshold
+ * (optimal_criterion is only lowered by an accepted leaf, math_model.py:195-198), applies the first pose of the
+ * accepted path -- or repeats the previous one when nothing beats the threshold -- counts repeated positions
+ * (stop at 2: "Recursive error") and tests is_on_target, all on the device; the host only reads one counter per tick.
+ *   init_state[N][3], target[N][2], origin[N][2], first_threshold[N] (control_criterion of the start pose)
+ *   out_log[N][max_ticks][5] = the 5-list each tick returns, out_ticks[N], out_status[N] (MPCB_LOOP_*) */
+MPCB_API int mpcb_full_closed_loop_host(mpcb_handle *h, int cost_kind, int H, int64_t N, const double *init_state,
+                               const double *target, const double *origin, const double *first_threshold,
+                               double eps, int max_ticks, double *out_log, int32_t *out_ticks, int32_t *out_status);
 
 /* Cross-rank reconciliation of a split tree: lexicographic (cost, index) minimum over the
  * ranks of an NCCL communicator (two 8-byte all-reduce-min rounds, exact for float64 costs

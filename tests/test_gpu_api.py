@@ -119,3 +119,37 @@ def test_full_module_leaf_cloud():
     np.testing.assert_allclose(y, yo, atol=2e-6)
     ok = Jo < 1e7
     np.testing.assert_allclose(J[ok], Jo[ok], atol=5e-3)
+
+
+def test_full_closed_loop_batch_matches_reference_ticks(golden):
+    """mpcb_full_closed_loop (run_batch): all scenarios of a grid in one batched loop vs the reference's own
+    tick-by-tick returns, incl. carried thresholds and the repeated-position stop."""
+    rm = importlib.import_module("diplomjourney_b200.run_math_model")
+    g = golden("full_h3")
+    for grid in ("g4x5", "g5x7", "g3x9"):
+        cases = [c for c in g["cases"] if c["script"] == "run_math_model.py" and c["grid"] == grid]
+        rm._backend = None
+        rm._grid_key = None
+        rm.vector_v, rm.vector_beta = np.array(cases[0]["vector_v"]), np.array(cases[0]["vector_beta"])
+        sc = np.array([[c["scenario"][k] for k in ("x_0", "y_0", "phi_0", "x_t", "y_t")] for c in cases], dtype=float)
+        nt = max(len(c["ticks"]) for c in cases)
+        r = rm.run_batch(sc, max_ticks=nt)
+        for i, c in enumerate(cases):
+            k_rep, knife_seen = 0, False
+            for t, tick in enumerate(c["ticks"]):
+                if t >= r["ticks"][i]:
+                    # our loop stopped (the fixture ran a fixed number of ticks): it must have had the reference's reason
+                    last = r["log"][i, t - 1]
+                    on_target = (c["scenario"]["x_t"] - last[0]) ** 2 + (c["scenario"]["y_t"] - last[1]) ** 2 <= 0.001
+                    assert (r["status"][i] == 0 and on_target) or (r["status"][i] == 1 and k_rep >= 2), (grid, i, t)
+                    break
+                knife_edge = (abs(tick["criterion_after"] - tick["threshold"]) < 1e-9 * tick["threshold"]
+                              and tick["criterion_after"] != tick["threshold"])
+                knife_seen = knife_seen or knife_edge               # ... and the stalls after it repeat that choice
+                cols = slice(0, 3) if knife_seen else slice(0, 5)   # accepted by 3e-13: controls may differ, pose not
+                np.testing.assert_allclose(r["log"][i, t, cols], tick["ret"][cols], rtol=0, atol=1e-12,
+                                           err_msg=f"{grid} scenario {i} tick {t}")
+                if t > 0 and tick["ret"][:2] == c["ticks"][t - 1]["ret"][:2]:
+                    k_rep += 1
+                elif t == 0 and tick["ret"][:2] == tick["state"][:2]:
+                    k_rep += 1
