@@ -37,7 +37,10 @@ oc = torch.empty(1, dtype=torch.float64, device="cuda"); oi = torch.empty(1, dty
 st = torch.tensor(x[:3].copy(), device="cuda"); tg = torch.tensor(x[3:5].copy(), device="cuda"); og = torch.tensor(x[:2].copy(), device="cuda")
 torch.cuda.synchronize()
 ext = torch.cuda.ExternalStream(s.stream)
-for H in [int(h) for h in os.environ.get("MPCB_SPLIT_H", "4,5").split(",")]:
+runs = [(int(h), 0) for h in os.environ.get("MPCB_SPLIT_H", "4,5").split(",")] + \
+       [(int(h), 1) for h in os.environ.get("MPCB_SPLIT_H_PRUNED", "").split(",") if h]
+for H, prune in runs:
+    s.set_option("prune", prune)
     # 256^5 = 1.1e12 leaves; 256^6 = 2.8e14 leaves is BASELINE config 5
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
@@ -54,8 +57,8 @@ for H in [int(h) for h in os.environ.get("MPCB_SPLIT_H", "4,5").split(",")]:
     st_ = s.stats()
     if rank == 0:
         leaves = s.S ** H
-        print(f"world={world} split-tree H={H} leaves={leaves:.3e} record={allrec[0]} time={float(tt[0]):.4f}s "
-              f"rate={leaves/float(tt[0]):.3e} rollouts/s refine(seg={st_['refine_segments']},cand={st_['refine_candidates']}) "
+        print(f"world={world} split-tree H={H} prune={prune} leaves={leaves:.3e} record={allrec[0]} time={float(tt[0]):.4f}s "
+              f"rate={leaves/float(tt[0]):.3e} rollouts/s refine(seg={st_['refine_segments']},cand={st_['refine_candidates']}) pruned_nodes={st_['pruned_units']}/{st_['units']} "
               f"[first H includes NCCL connection setup]", flush=True)
 if rank == 0:
     print(f"world={world} parity={'OK' if ok else 'FAIL'}", flush=True)
