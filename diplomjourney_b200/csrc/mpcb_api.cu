@@ -94,7 +94,6 @@ struct mpcb_handle_s {
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
     size_t pin_in_cap = 0, pin_out_cap = 0;
     mpcb_stats stats{};
-    unsigned long long last_counters_pending = 0;
 };
 
 namespace {
@@ -142,14 +141,14 @@ int make_plan(mpcb_handle *h, int mode, int H, long long N, long long i0_begin, 
         pl.u_begin = 0; pl.u_end = S; pl.leaves_per_solve = S;
         return MPCB_OK;
     }
-    unsigned long long leaves, sub;
+    unsigned long long leaves = 0, sub = 1;
     if (!pow_checked(S, H, leaves)) return fail(h, MPCB_ERR_TOO_LARGE, "S^H = %llu^%d exceeds int64", S, H);
     pow_checked(S, H - 1, sub);
     if (i0_end < 0) { i0_begin = 0; i0_end = (long long)S; }
     if (i0_begin < 0 || i0_end > (long long)S || i0_begin > i0_end)
         return fail(h, MPCB_ERR_INVALID, "bad first-control range [%lld,%lld) for S=%llu", i0_begin, i0_end, S);
     int algo = algo_req == MPCB_ALGO_AUTO ? h->algo : algo_req;
-    unsigned long long parents = H >= 2 ? sub / 1 : 0;   // S^(H-1)
+    const unsigned long long parents = H >= 2 ? sub : 0;   // S^(H-1) depth-(H-1) nodes
     if (algo == MPCB_ALGO_AUTO)
         algo = (H >= 2 && (unsigned __int128)parents * (unsigned long long)N >= 32768) ? MPCB_ALGO_PREFIX
                                                                                        : MPCB_ALGO_LEAFWALK;

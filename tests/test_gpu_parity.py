@@ -16,7 +16,6 @@ pytestmark = pytest.mark.gpu
 
 nat = pytest.importorskip("diplomjourney_b200._native")
 
-MODES = {"full": nat.MODE_FULL, "held": nat.MODE_HELD}
 COSTS = {C.COST_MM: nat.COST_MM, C.COST_TREE: nat.COST_TREE}
 L, DT, VMIN = C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"]
 
