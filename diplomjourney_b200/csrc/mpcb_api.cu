@@ -181,6 +181,10 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
     }
     a.u_begin = pl.u_begin; a.u_end = pl.u_end;
     a.i0_begin = (int)pl.i0_begin; a.i0_end = (int)pl.i0_end;
+    {   // digits of kThreads in base S over H positions (leafwalk's incremental index decode)
+        unsigned long long r = kThreads;
+        for (int k = H - 1; k >= 0; --k) { a.step_digits[k] = mode == MPCB_MODE_FULL ? (unsigned)(r % S) : 0u; r = mode == MPCB_MODE_FULL ? r / S : 0; }
+    }
     a.tile_units = pl.prefix ? kThreads : kThreads * kLeafPerThread;
     a.lw_smem = (!pl.prefix && mode == MPCB_MODE_FULL && h->g.S <= 4096) ? 1 : 0;
 }

@@ -455,14 +455,19 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
 // (heading relative to the start heading, so sin.approx/cos.approx see |psi| <~ 1), score.
 // KIND: 0 = FULL with 64-bit leaf indices, 1 = FULL with every index < 2^32, 2 = HELD (control j held).
 // SMEM: ctl points into shared memory (FULL trees whose {dphi, s} table fits).
-template <bool HEAD, int KIND, bool SMEM = false>
+// HT > 0: horizon known at compile time (the walk is fully unrolled, divisors live in uniform registers);
+// HT = 0: run-time horizon a.H.
+template <bool HEAD, int KIND, bool SMEM = false, int HT = 0>
 __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveParams &P, const ParentRegs &pr,
                                                const float2 *__restrict__ ctl, unsigned long long j,
                                                float &xi, float &eta, float &psi) {
     xi = 0.f; eta = 0.f; psi = 0.f;
     unsigned long long rem = j;
     unsigned rem32 = (unsigned)j;
-    for (int k = 0; k < a.H; ++k) {
+    const int H = HT > 0 ? HT : a.H;
+#pragma unroll
+    for (int k = 0; k < (HT > 0 ? HT : kMaxH); ++k) {
+        if (HT == 0 && k >= H) break;
         unsigned c;
         if (KIND == 2) c = (unsigned)j;
         else if (KIND == 1) { c = a.fd32[k].div(rem32); rem32 -= c * a.fd32[k].d; }
@@ -483,17 +488,35 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
     return L;
 }
 
-template <int PASS, bool HEAD, int KIND>
-__global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) {
-    extern __shared__ float2 s_ctl[];        // FULL trees: the {dphi, s} table, when it fits (a.lw_smem)
-    __shared__ double s_J[kThreads / 32];
-    __shared__ long long s_j[kThreads / 32];
-    const int tid = threadIdx.x;
-    const bool staged = KIND != 2 && a.lw_smem;
-    if (staged) {
-        for (int i = tid; i < a.g.S; i += kThreads) s_ctl[i] = __ldg(a.g.ctl32 + i);
-        __syncthreads();
+// FULL tree, indices < 2^32, horizon HT known: the control digits of the thread's leaf are kept in registers and
+// advanced by kThreads (mixed-radix add with carries) instead of being re-derived by divisions for every leaf.
+template <bool HEAD, bool SMEM, int HT>
+__device__ __forceinline__ float leafwalk_eval_digits(const SolveParams &P, const ParentRegs &pr,
+                                                      const float2 *__restrict__ ctl, const unsigned (&c)[HT]) {
+    float xi = 0.f, eta = 0.f, psi = 0.f;
+#pragma unroll
+    for (int k = 0; k < HT; ++k) {
+        float2 t = SMEM ? ctl[c[k]] : __ldg(ctl + c[k]);
+        psi += t.x;
+        float sn, cs;
+        __sincosf(psi, &sn, &cs);
+        xi = __fmaf_rn(t.y, cs, xi);
+        eta = __fmaf_rn(t.y, sn, eta);
     }
+    const float r = __fmaf_rn(xi, xi, eta * eta);
+    const float g = 3.16227766016837952f * psi;
+    float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
+                                    : leaf_val<HEAD, false>(xi, eta, r, g, pr);
+    if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
+        L = (float)(P.special - P.e0 * P.e0) + (HEAD ? g * (g - pr.h2) : 0.f);
+    return L;
+}
+
+// the work loop of one CTA; HT as above
+template <int PASS, bool HEAD, int KIND, int HT>
+__device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 *s_ctl, bool staged, double *s_J,
+                                              long long *s_j) {
+    const int tid = threadIdx.x;
     const unsigned long long nwork =
         PASS == 1 ? a.total_segs : (unsigned long long)(*a.work_count) * a.tps;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -511,21 +534,63 @@ __global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) 
         double bJ = INFINITY; long long bj = -1;
         for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
             const unsigned long long j0 = a.u_begin + tile * (unsigned long long)(kThreads * kLeafPerThread) + tid;
-            // kLeafPerThread leaves per thread, strided by the CTA width (coalesced table reads)
+            if constexpr (PASS == 1 && KIND == 1 && HT > 0) {
+                // digits of j0 once, then +kThreads per leaf
+                unsigned c[HT];
+                unsigned rem32 = (unsigned)j0;
+#pragma unroll
+                for (int d = 0; d < HT; ++d) { c[d] = a.fd32[d].div(rem32); rem32 -= c[d] * a.fd32[d].d; }
+                const unsigned S = (unsigned)a.g.S, jend = (unsigned)a.u_end;
+                unsigned j32 = (unsigned)j0;
 #pragma unroll 4
-            for (int k = 0; k < kLeafPerThread; ++k) {
-                const unsigned long long j = j0 + (unsigned)k * kThreads;
-                if (j >= a.u_end) break;
-                float xi, eta, psi;
-                const float L = smem ? leafwalk_eval<HEAD, KIND, true>(a, P, pr, ctl, j, xi, eta, psi)
-                                     : leafwalk_eval<HEAD, KIND, false>(a, P, pr, ctl, j, xi, eta, psi);
-                if (PASS == 1) best = fminf(best, L);
-                else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
+                for (int k = 0; k < kLeafPerThread; ++k) {
+                    if (j32 >= jend) break;
+                    const float L = smem ? leafwalk_eval_digits<HEAD, true, HT>(P, pr, ctl, c)
+                                         : leafwalk_eval_digits<HEAD, false, HT>(P, pr, ctl, c);
+                    best = fminf(best, L);
+                    j32 += kThreads;
+                    unsigned carry = 0;
+#pragma unroll
+                    for (int d = HT - 1; d >= 0; --d) {
+                        unsigned v = c[d] + a.step_digits[d] + carry;
+                        carry = v >= S ? 1u : 0u;
+                        c[d] = v - (carry ? S : 0u);
+                    }
+                }
+            } else {
+                // kLeafPerThread leaves per thread, strided by the CTA width (coalesced table reads)
+#pragma unroll 4
+                for (int k = 0; k < kLeafPerThread; ++k) {
+                    const unsigned long long j = j0 + (unsigned)k * kThreads;
+                    if (j >= a.u_end) break;
+                    float xi, eta, psi;
+                    const float L = smem ? leafwalk_eval<HEAD, KIND, true, HT>(a, P, pr, ctl, j, xi, eta, psi)
+                                         : leafwalk_eval<HEAD, KIND, false, HT>(a, P, pr, ctl, j, xi, eta, psi);
+                    if (PASS == 1) best = fminf(best, L);
+                    else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
+                }
             }
         }
         if (PASS == 1) publish_segmin(a, seg, base + (double)best);
         else publish_best(a, n, bJ, bj, s_J, s_j);
     }
+}
+
+template <int PASS, bool HEAD, int KIND>
+__global__ void __launch_bounds__(kThreads) leafwalk_kernel(const LaunchArgs a) {
+    extern __shared__ float2 s_ctl[];        // FULL trees: the {dphi, s} table, when it fits (a.lw_smem)
+    __shared__ double s_J[kThreads / 32];
+    __shared__ long long s_j[kThreads / 32];
+    const bool staged = KIND != 2 && a.lw_smem;
+    if (staged) {
+        for (int i = threadIdx.x; i < a.g.S; i += kThreads) s_ctl[i] = __ldg(a.g.ctl32 + i);
+        __syncthreads();
+    }
+    // pass 1 is specialised for the common horizons (the reference's 3, and 2/4); pass 2 is rare
+    if (PASS == 1 && a.H == 3) leafwalk_body<PASS, HEAD, KIND, 3>(a, s_ctl, staged, s_J, s_j);
+    else if (PASS == 1 && a.H == 4) leafwalk_body<PASS, HEAD, KIND, 4>(a, s_ctl, staged, s_J, s_j);
+    else if (PASS == 1 && a.H == 2) leafwalk_body<PASS, HEAD, KIND, 2>(a, s_ctl, staged, s_J, s_j);
+    else leafwalk_body<PASS, HEAD, KIND, 0>(a, s_ctl, staged, s_J, s_j);
 }
 
 // ------------------------------------------------------------------------------------ dump

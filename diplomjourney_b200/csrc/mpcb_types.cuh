@@ -90,6 +90,7 @@ struct LaunchArgs {
     FastDiv64 fd[kMaxH];        // fd[k].d = S^(H-1-k)
     FastDiv32 fd32[kMaxH];      // same divisors, valid when idx32 != 0 (every index and divisor < 2^32)
     int idx32;
+    unsigned step_digits[kMaxH]; // base-S digits of kThreads (most significant first): leafwalk advances a leaf index by kThreads
     int lw_smem;                // leafwalk FULL: stage ctl32 in shared memory (S <= 4096)
     unsigned tile_units;        // units per tile: kThreads (prefix) or kThreads*kLeafPerThread (leafwalk)
     int mode, H, cost_kind, refine;
