@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
 template <bool HEAD, int KIND, bool SMEM = false, int HT = 0>
 __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveParams &P, const ParentRegs &pr,
                                                const float2 *__restrict__ ctl, unsigned long long j,
-                                               float &xi, float &eta, float &psi) {
+                                               float &xi, float &eta, float &psi, float Lsp) {
     xi = 0.f; eta = 0.f; psi = 0.f;
     unsigned long long rem = j;
     unsigned rem32 = (unsigned)j;
@@ -484,7 +484,7 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
     float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
                                     : leaf_val<HEAD, false>(xi, eta, r, g, pr);
     if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
-        L = (float)(P.special - P.e0 * P.e0) + (HEAD ? g * (g - pr.h2) : 0.f);
+        L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
     return L;
 }
 
@@ -492,7 +492,7 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
 // advanced by kThreads (mixed-radix add with carries) instead of being re-derived by divisions for every leaf.
 template <bool HEAD, bool SMEM, int HT>
 __device__ __forceinline__ float leafwalk_eval_digits(const SolveParams &P, const ParentRegs &pr,
-                                                      const float2 *__restrict__ ctl, const unsigned (&c)[HT]) {
+                                                      const float2 *__restrict__ ctl, const unsigned (&c)[HT], float Lsp) {
     float xi = 0.f, eta = 0.f, psi = 0.f;
 #pragma unroll
     for (int k = 0; k < HT; ++k) {
@@ -508,7 +508,7 @@ __device__ __forceinline__ float leafwalk_eval_digits(const SolveParams &P, cons
     float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
                                     : leaf_val<HEAD, false>(xi, eta, r, g, pr);
     if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
-        L = (float)(P.special - P.e0 * P.e0) + (HEAD ? g * (g - pr.h2) : 0.f);
+        L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
     return L;
 }
 
@@ -526,6 +526,7 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
         if (P.flags & kFlagSkip) continue;
         ParentRegs pr;
         const double base = start_as_parent(P, pr);
+        const float Lsp = (float)(P.special - P.e0 * P.e0);     // leaf part of an "on the line origin" leaf
         const bool smem = staged && !(P.flags & kFlagSlow);
         const float2 *ctl = smem ? s_ctl : ((P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32);
         const float thr = PASS == 2 ? __double2float_ru(a.tau[n] - base) : 0.f;
@@ -545,8 +546,8 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
 #pragma unroll 4
                 for (int k = 0; k < kLeafPerThread; ++k) {
                     if (j32 >= jend) break;
-                    const float L = smem ? leafwalk_eval_digits<HEAD, true, HT>(P, pr, ctl, c)
-                                         : leafwalk_eval_digits<HEAD, false, HT>(P, pr, ctl, c);
+                    const float L = smem ? leafwalk_eval_digits<HEAD, true, HT>(P, pr, ctl, c, Lsp)
+                                         : leafwalk_eval_digits<HEAD, false, HT>(P, pr, ctl, c, Lsp);
                     best = fminf(best, L);
                     j32 += kThreads;
                     unsigned carry = 0;
@@ -564,8 +565,8 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
                     const unsigned long long j = j0 + (unsigned)k * kThreads;
                     if (j >= a.u_end) break;
                     float xi, eta, psi;
-                    const float L = smem ? leafwalk_eval<HEAD, KIND, true, HT>(a, P, pr, ctl, j, xi, eta, psi)
-                                         : leafwalk_eval<HEAD, KIND, false, HT>(a, P, pr, ctl, j, xi, eta, psi);
+                    const float L = smem ? leafwalk_eval<HEAD, KIND, true, HT>(a, P, pr, ctl, j, xi, eta, psi, Lsp)
+                                         : leafwalk_eval<HEAD, KIND, false, HT>(a, P, pr, ctl, j, xi, eta, psi, Lsp);
                     if (PASS == 1) best = fminf(best, L);
                     else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
                 }
@@ -603,11 +604,12 @@ __global__ void __launch_bounds__(kThreads) leafwalk_dump_kernel(const LaunchArg
     const double base = start_as_parent(P, pr);
     const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
     const float c0 = (float)cos(P.phi0), s0 = (float)sin(P.phi0);
+    const float Lsp = (float)(P.special - P.e0 * P.e0);
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < a.dump_count;
          i += (unsigned long long)gridDim.x * kThreads) {
         float xi, eta, psi;
-        const float L = a.mode == 1 ? leafwalk_eval<HEAD, 2>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi)
-                                    : leafwalk_eval<HEAD, 0>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi);
+        const float L = a.mode == 1 ? leafwalk_eval<HEAD, 2>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi, Lsp)
+                                    : leafwalk_eval<HEAD, 0>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi, Lsp);
         a.dump[i] = make_float4((float)P.xs + (c0 * xi - s0 * eta), (float)P.ys + (s0 * xi + c0 * eta),
                                 (float)P.phi0 + psi, L);
         jrel[i] = base + (double)L;
