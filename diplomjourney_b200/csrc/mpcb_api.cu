@@ -414,7 +414,7 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
 
     int launches = 0;
-    CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, pl.prefix ? 1 : 0,
+    CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, (pl.prefix ? 1 : 0) | (mode == MPCB_MODE_HELD ? 2 : 0),
                    h->g.smax, h->g.dphimax, h->tol_scale, h->sp.as<SolveParams>())); ++launches;
     if (a.prune) {
         CK(launch_probe(h->stream, a, h->sms)); ++launches;
@@ -589,7 +589,7 @@ int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int al
     CK(h->dump_rec.ensure(sizeof(float4) * count));
     CK(h->dump_j.ensure(sizeof(double) * count));
     CK(launch_prep(st, 1, h->in_state.as<double>(), h->in_target.as<double>(), h->in_origin.as<double>(), nullptr,
-                   h->in_flags.as<uint8_t>(), cost_kind, H, pl.prefix ? 1 : 0, h->g.smax, h->g.dphimax, h->tol_scale,
+                   h->in_flags.as<uint8_t>(), cost_kind, H, (pl.prefix ? 1 : 0) | (mode == MPCB_MODE_HELD ? 2 : 0), h->g.smax, h->g.dphimax, h->tol_scale,
                    h->sp.as<SolveParams>()));
     a.sp = h->sp.as<SolveParams>();
     a.dump = h->dump_rec.as<float4>();

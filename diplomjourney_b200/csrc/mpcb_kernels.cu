@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kThreads) prefix_dump_kernel(const LaunchArgs 
 // Raw inputs -> SolveParams (float64), incl. the per-solve error window of the refinement pass.
 __global__ void prep_kernel(long long N, const double *__restrict__ state, const double *__restrict__ target,
                             const double *__restrict__ origin, const double *__restrict__ threshold,
-                            const uint8_t *__restrict__ flags, int cost_kind, int H, int prefix,
+                            const uint8_t *__restrict__ flags, int cost_kind, int H, int kind,
                             double smax, double dphimax, double tol_scale, SolveParams *__restrict__ out) {
     const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -672,7 +672,10 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     P.hp0 = P.wh * (P.theta - P.phi0);
     P.Kbase = kWd * P.d0 + P.e0 * P.e0 + P.hp0 * P.hp0;
     P.special = 1.0e6 * P.wl * P.wl;
-    int f = flags ? (flags[n] & kFlagSlow) : 0;
+    // kind: bit0 = prefix algorithm, bit1 = HELD tree.  The slow-down override belongs to the online (HELD)
+    // controller (math_model_tree.py:312-316); FULL solves ignore the flag.
+    const bool prefix = (kind & 1) != 0, held = (kind & 2) != 0;
+    int f = (flags && held) ? (flags[n] & kFlagSlow) : 0;
     if (flags && (flags[n] & 2)) f |= kFlagSkip;          // MPCB_FLAG_SKIP
     if (P.xs == P.ox && P.ys == P.oy) f |= kFlagStartIsOrigin;
     // error model of the fp32 leaf part

@@ -66,7 +66,8 @@ typedef enum {
 #define MPCB_MAX_H 8
 
 /* per-solve flags (uint8 per solve) */
-#define MPCB_FLAG_SLOW 1 /* steps_for_slowing > 0: every velocity := max(min(V), v_min), math_model_tree.py:312-316 */
+#define MPCB_FLAG_SLOW 1 /* steps_for_slowing > 0: every velocity := max(min(V), v_min), math_model_tree.py:312-316;
+                            honoured by HELD solves only (the FULL scripts have no slow-down) */
 #define MPCB_FLAG_SKIP 2 /* do not solve this entry (a robot of a batch that has already stopped): index -1, cost NaN */
 
 MPCB_API int mpcb_version(void);

@@ -323,3 +323,19 @@ def test_branch_and_bound_is_exact(solver, cost):
     finally:
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
+
+
+def test_slow_flag_is_held_only(solver):
+    """MPCB_FLAG_SLOW is the online controller's override; a FULL solve must ignore it (both algorithms)."""
+    V, B = [0.2, 0.6, 1.0], np.linspace(-1, 1, 5)
+    solver.set_grid(V, B, L, DT, VMIN)
+    s = C.random_scenarios(1, 3)[0]
+    ref = K.solve_full(s[:3], s[3:], s[:2], V, B, 3, C.COST_MM)
+    for algo in (nat.ALGO_LEAFWALK, nat.ALGO_PREFIX):
+        solver.set_option("algo", algo)
+        r = solver.solve(nat.MODE_FULL, nat.COST_MM, 3, s[:3], s[3:5], s[:2], flags=nat.FLAG_SLOW)
+        assert r["index"][0] == ref["index"] and r["cost"][0] == pytest.approx(ref["cost"], rel=1e-12)
+    solver.set_option("algo", nat.ALGO_AUTO)
+    held = solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, s[:3], s[3:5], s[:2], flags=nat.FLAG_SLOW)
+    o = K.solve_held(s[:3], s[3:], s[:2], V, B, 3, C.COST_TREE, slow=True)
+    assert held["index"][0] == o["index"] and held["first_control"][0, 0] == 0.4     # max(min V, v_min)
