@@ -686,7 +686,8 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     if (!prefix && near) f |= kFlagNear;
     const double E = fabs(P.e0) + P.wl * Rtot, Hh = fabs(P.hp0) + P.wh * H * dphimax, Q = P.wl * Rl;
     double M = kWd * Rl * 16.0 + 4.0 * Q * (2.0 * E + Q) + 4.0 * Gl * (Gl + 2.0 * Hh);
-    if (!prefix) M += kWd * Rtot * 8.0;            // sin.approx / cos.approx absolute error per step
+    // sin.approx / cos.approx: absolute error 2^-21.4 on [-pi, pi], growing with the argument beyond it
+    if (!prefix) M += kWd * Rtot * 8.0 * fmax(1.0, H * dphimax / 3.141592653589793);
     P.tol = 2.0 * M * 1.1920928955078125e-07 * tol_scale;
     P.flags = f; P.pad = 0;
     out[n] = P;

@@ -263,7 +263,7 @@ def _eps_model(s, origin, H, cost, prefix, smax, dphimax):
     E, Hh, Q = abs(e0) + wl * Rtot, abs(hp0) + wh * H * dphimax, wl * Rl
     M = 1e4 * Rl * 16 + 4 * Q * (2 * E + Q) + 4 * Gl * (Gl + 2 * Hh)
     if not prefix:
-        M += 1e4 * Rtot * 8
+        M += 1e4 * Rtot * 8 * max(1.0, H * dphimax / math.pi)
     return M * 2.0 ** -23
 
 
@@ -339,3 +339,18 @@ def test_slow_flag_is_held_only(solver):
     held = solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, s[:3], s[3:5], s[:2], flags=nat.FLAG_SLOW)
     o = K.solve_held(s[:3], s[3:], s[:2], V, B, 3, C.COST_TREE, slow=True)
     assert held["index"][0] == o["index"] and held["first_control"][0, 0] == 0.4     # max(min V, v_min)
+
+
+def test_large_heading_changes_stay_exact(solver):
+    """Short wheelbase => up to ~1.7 rad of heading change per step: sin.approx/cos.approx leave their accurate
+    range in the leafwalk kernel; the window model widens with it and the result stays the float64 argmin."""
+    V, B = [0.3, 1.0], np.linspace(-1.0, 1.0, 7)
+    Lshort = 0.05
+    for algo in (nat.ALGO_LEAFWALK, nat.ALGO_PREFIX):
+        solver.set_option("algo", algo)
+        solver.set_grid(V, B, Lshort, DT, VMIN)
+        sc = C.random_scenarios(12, 909)
+        res = solver.solve(nat.MODE_FULL, nat.COST_MM, 4, sc[:, :3], sc[:, 3:5], sc[:, :2])
+        for i, s in enumerate(sc):
+            _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, 4, C.COST_MM, L=Lshort), 4)
+    solver.set_option("algo", nat.ALGO_AUTO)
