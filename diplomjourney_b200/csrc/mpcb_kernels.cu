@@ -23,9 +23,6 @@
 #ifndef MPCB_UNROLL
 #define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (measured best of 1/2/4/8, profiles/r1b_variants.txt)
 #endif
-#ifndef MPCB_MINB
-#define MPCB_MINB 4     // resident CTAs per SM the pass-1 kernel is compiled for (64 regs; 5/6/8 measured slower)
-#endif
 
 #include <cfloat>
 #include <cmath>
@@ -353,7 +350,7 @@ __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict
 // window are skipped lane by lane (a queue that compacts the survivors across tiles was measured 1.3-4x SLOWER:
 // it serialises the float64 set-up and the fp32 pair loop that otherwise overlap between warps).
 template <int PASS, bool HEAD, bool PRUNE = false>
-__global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_kernel(const LaunchArgs a) {
+__global__ void __launch_bounds__(PASS == 1 ? kPrefixTile : kThreads, 1) prefix_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
     __shared__ double s_J[kThreads / 32];
     __shared__ long long s_j[kThreads / 32];
@@ -365,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
     const float4 *__restrict__ gtab = PASS == 1 ? a.g.leaf32p : a.g.leaf32;
     auto chunk_f4 = [&](int cn) { return PASS == 1 ? 2 * ((cn + 1) >> 1) : cn; };
     if (single) {
-        for (int i = tid; i < chunk_f4(S); i += kThreads) s_leaf[i] = __ldg(gtab + i);
+        for (int i = tid; i < chunk_f4(S); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
         __syncthreads();
     }
     const unsigned long long nwork =
@@ -380,8 +377,9 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
         if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
         double segbest = INFINITY;
         double bJ = INFINITY; long long bj = -1;
-        for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
-            const unsigned long long p = a.u_begin + tile * kThreads + tid;
+        // a tile is kPrefixTile consecutive nodes; the CTA covers it in blockDim.x-wide slices
+        for (unsigned long long slice = tile_lo * (kPrefixTile / blockDim.x); slice < tile_hi * (kPrefixTile / blockDim.x); ++slice) {
+            const unsigned long long p = a.u_begin + slice * blockDim.x + tid;
             const bool in_range = p < a.u_end;
             ParentRegs pr = {};
             bool near = false, unmoved = false;
@@ -408,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 1 ? MPCB_MINB : 1) prefix_ke
                 const int cn = min(kLeafChunk, S - c0);
                 if (!single) {
                     __syncthreads();
-                    for (int i = tid; i < chunk_f4(cn); i += kThreads) s_leaf[i] = __ldg(gtab + c0 + i);
+                    for (int i = tid; i < chunk_f4(cn); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
                     __syncthreads();
                 }
                 if (!active) continue;
@@ -797,20 +795,21 @@ static size_t prefix_smem(const LaunchArgs &a) {
 }
 
 template <typename K>
-static int resident_ctas(K kernel, size_t smem) {
+static int resident_ctas(K kernel, size_t smem, int threads) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
     return n;
 }
 
 template <typename K>
-static cudaError_t launch_persistent(K kernel, const LaunchArgs &a, int pass, size_t smem, int sms, cudaStream_t st) {
+static cudaError_t launch_persistent(K kernel, const LaunchArgs &a, int pass, size_t smem, int sms, cudaStream_t st,
+                                     int threads = kThreads) {
     // pass 1: one CTA per resident slot, striding over the segments; pass 2: same grid over the
     // device-side work list (its length is not known on the host)
     if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int slots = sms * resident_ctas(kernel, smem);
+    const int slots = sms * resident_ctas(kernel, smem, threads);
     const int grid = pass == 1 ? (int)(a.total_segs < (unsigned long long)slots ? a.total_segs : slots) : slots;
-    kernel<<<grid, kThreads, smem, st>>>(a);
+    kernel<<<grid, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -819,11 +818,11 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
     if (prefix) {
         const size_t sm = prefix_smem(a);
         if (pass == 1 && a.prune)
-            return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
-                        : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
+            return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st, kPrefixTile)
+                        : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st, kPrefixTile);
         if (pass == 1)
-            return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st)
-                        : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st);
+            return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixTile)
+                        : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixTile);
         return head ? launch_persistent(prefix_kernel<2, true>, a, pass, sm, sms, st)
                     : launch_persistent(prefix_kernel<2, false>, a, pass, sm, sms, st);
     }
