@@ -185,7 +185,7 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
         unsigned long long r = kThreads;
         for (int k = H - 1; k >= 0; --k) { a.step_digits[k] = mode == MPCB_MODE_FULL ? (unsigned)(r % S) : 0u; r = mode == MPCB_MODE_FULL ? r / S : 0; }
     }
-    a.tile_units = pl.prefix ? kPrefixTile : kThreads * kLeafPerThread;
+    a.tile_units = pl.prefix ? kThreads : kThreads * kLeafPerThread;
     a.lw_smem = (!pl.prefix && mode == MPCB_MODE_FULL && h->g.S <= 4096) ? 1 : 0;
 }
 

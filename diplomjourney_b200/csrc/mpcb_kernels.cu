@@ -21,7 +21,7 @@
 #include "mpcb_types.cuh"
 
 #ifndef MPCB_UNROLL
-#define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (measured best of 1/2/4/8, profiles/r1b_variants.txt)
+#define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (4..16 are within 1 %, profiles/r1b_variants.txt)
 #endif
 
 #include <cfloat>
@@ -350,7 +350,8 @@ __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict
 // window are skipped lane by lane (a queue that compacts the survivors across tiles was measured 1.3-4x SLOWER:
 // it serialises the float64 set-up and the fp32 pair loop that otherwise overlap between warps).
 template <int PASS, bool HEAD, bool PRUNE = false>
-__global__ void __launch_bounds__(PASS == 1 ? kPrefixTile : kThreads, 1) prefix_kernel(const LaunchArgs a) {
+__global__ void __launch_bounds__((PASS == 1 && !PRUNE) ? kPrefixCta : kThreads, (PASS == 1 && PRUNE) ? 4 : 1)
+prefix_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
     __shared__ double s_J[kThreads / 32];
     __shared__ long long s_j[kThreads / 32];
@@ -365,11 +366,25 @@ __global__ void __launch_bounds__(PASS == 1 ? kPrefixTile : kThreads, 1) prefix_
         for (int i = tid; i < chunk_f4(S); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
         __syncthreads();
     }
+    // pass 1: one work item = kPrefixCta/kThreads consecutive 256-node tiles of one solve, one per thread group;
+    // pass 2: one work item = one listed tile (256 threads)
+    // (the exhaustive kernel runs 1024-thread CTAs = 4 groups; the pruned one 256-thread CTAs = 1 group, so that a
+    //  fully cut tile costs nothing more than its set-up)
+    const unsigned groups = blockDim.x / kThreads;
+    const unsigned long long qps = (a.tiles_per_solve + groups - 1) / groups;
     const unsigned long long nwork =
-        PASS == 1 ? a.total_segs : (unsigned long long)(*a.work_count) * a.tps;
+        PASS == 1 ? (unsigned long long)a.N * qps : (unsigned long long)(*a.work_count) * a.tps;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
-        decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
+        if (PASS == 1) {
+            n = (long long)(w / qps);
+            const unsigned long long tile = (w - (unsigned long long)n * qps) * groups + (tid / kThreads);
+            tile_lo = tile;
+            tile_hi = tile < a.tiles_per_solve ? tile + 1 : tile;          // groups past the last tile idle
+            seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
+        } else {
+            decode_work<PASS>(a, w, seg, n, tile_lo, tile_hi);
+        }
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;               // a robot that has already stopped (uniform per work item)
         const bool origin_case = (P.flags & kFlagStartIsOrigin) != 0;
@@ -377,10 +392,10 @@ __global__ void __launch_bounds__(PASS == 1 ? kPrefixTile : kThreads, 1) prefix_
         if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
         double segbest = INFINITY;
         double bJ = INFINITY; long long bj = -1;
-        // a tile is kPrefixTile consecutive nodes; the CTA covers it in blockDim.x-wide slices
-        for (unsigned long long slice = tile_lo * (kPrefixTile / blockDim.x); slice < tile_hi * (kPrefixTile / blockDim.x); ++slice) {
-            const unsigned long long p = a.u_begin + slice * blockDim.x + tid;
-            const bool in_range = p < a.u_end;
+        {
+            const unsigned long long tile = tile_lo;
+            const unsigned long long p = a.u_begin + tile * kThreads + (tid % kThreads);
+            const bool in_range = tile < tile_hi && p < a.u_end;
             ParentRegs pr = {};
             bool near = false, unmoved = false;
             double base = 0.0, lb = -INFINITY;
@@ -818,11 +833,11 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
     if (prefix) {
         const size_t sm = prefix_smem(a);
         if (pass == 1 && a.prune)
-            return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st, kPrefixTile)
-                        : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st, kPrefixTile);
+            return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
+                        : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
         if (pass == 1)
-            return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixTile)
-                        : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixTile);
+            return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixCta)
+                        : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixCta);
         return head ? launch_persistent(prefix_kernel<2, true>, a, pass, sm, sms, st)
                     : launch_persistent(prefix_kernel<2, false>, a, pass, sm, sms, st);
     }

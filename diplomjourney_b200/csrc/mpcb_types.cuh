@@ -16,8 +16,9 @@ namespace mpcb {
 #define MPCB_THREADS 256
 #endif
 constexpr int kThreads = MPCB_THREADS;   // threads per CTA; one "unit" (leaf or depth-(H-1) node) per thread
-constexpr int kPrefixTile = 1024;  // depth-(H-1) nodes per prefix tile; pass 1 runs it with one 1024-thread CTA per SM
-                                   // (measured +5 % over 4 x 256), pass 2 walks the same tile with 256 threads
+constexpr int kPrefixCta = 1024;   // pass 1 of the prefix kernel runs ONE 1024-thread CTA per SM (measured +4-6 % over
+                                   // 4 x 256); it covers four 256-node tiles at a time, so segments, the refinement
+                                   // pass and the work list keep their 256-node granularity
 constexpr int kMaxH = 8;
 constexpr int kLeafChunk = 1024;   // float4 entries of the per-control leaf table staged in shared memory
 
