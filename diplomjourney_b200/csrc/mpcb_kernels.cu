@@ -463,6 +463,96 @@ prefix_kernel(const LaunchArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------ prefix, pruned (pass 1)
+// Exact branch-and-bound (option prune).  Cutting nodes lane by lane leaves warps with one or two live lanes --
+// the promising nodes are scattered (a few steering directions per speed) -- so every WARP runs on its own:
+// it sets up 32 nodes at a time in float64, tests each node's lower bound against the solve's running upper bound,
+// appends the survivors to a warp-private shared-memory queue, and whenever 32 survivors are queued (and at the
+// end) hands one to each lane and runs the dense pair loop.  The pair table is read straight from global memory
+// (warp-uniform addresses, L1/L2 hits: ~6 % slower per pair than shared memory, tools/ubench/mix2.cu) so that no
+// CTA barrier ties the warps together.  Results are identical to the exhaustive kernel.
+struct __align__(8) QEntry {
+    ParentRegs pr;
+    float Lspecial;
+    unsigned seg;
+    double base;
+    long long n;
+    unsigned flags;      // bit0 near, bit1 special
+    unsigned pad;
+};
+constexpr int kWarpQueue = 64;
+
+template <bool HEAD>
+__global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const LaunchArgs a) {
+    extern __shared__ unsigned char s_raw[];
+    QEntry *q = reinterpret_cast<QEntry *>(s_raw) + (threadIdx.x >> 5) * kWarpQueue;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int S = a.g.S, npairs = (S + 1) >> 1;
+    const float4 *__restrict__ tab = a.g.leaf32p;
+    int count = 0;                                            // queue fill (warp-uniform)
+
+    auto drain = [&](int m) {
+        if (lane < m) {
+            const QEntry e = q[lane];
+            const float best = e.flags ? prefix_min_loop_scalar<HEAD>(tab, npairs, e.pr, (e.flags & 1) != 0,
+                                                                      (e.flags & 2) != 0, e.Lspecial, INFINITY)
+                                       : prefix_min_loop_far2<HEAD>(tab, npairs, e.pr, INFINITY);
+            const double v = e.base + (double)best;
+            if (v < INFINITY) {
+                atomicMin(reinterpret_cast<unsigned long long *>(a.segmin) + e.seg, ordered_key(v));
+                // this node's best fp32 value + its error bound is >= a true leaf cost: tighten the upper bound
+                atomicMin(a.ub + e.n, ordered_key(v + 0.5 * a.sp[e.n].tol));
+            }
+        }
+        __syncwarp();
+        const int rest = count - m;                           // < 32: move the tail to the front
+        QEntry t;
+        if (lane < rest) t = q[m + lane];
+        __syncwarp();
+        if (lane < rest) q[lane] = t;
+        __syncwarp();
+        count = rest;
+    };
+
+    const unsigned long long wtps = (a.u_end - a.u_begin + 31) / 32;      // 32-node warp tiles per solve
+    const unsigned long long nww = (unsigned long long)a.N * wtps;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const unsigned long long GW = (unsigned long long)gridDim.x * (kThreads / 32);
+    for (unsigned long long ww = gw; ww < nww; ww += GW) {
+        const long long n = (long long)(ww / wtps);
+        const unsigned long long wt = ww - (unsigned long long)n * wtps;
+        const SolveParams &P = a.sp[n];
+        if (P.flags & kFlagSkip) continue;
+        const unsigned long long tile = wt / (kThreads / 32);
+        const unsigned seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
+        const unsigned long long p = a.u_begin + wt * 32 + lane;
+        const bool in_range = p < a.u_end;
+        ParentRegs pr = {};
+        bool near = false, unmoved = false;
+        double base = 0.0, lb = -INFINITY;
+        if (in_range) base = parent_setup(a, P, p, pr, near, unmoved, &lb);
+        const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + 2.0 * P.tol;
+        const bool cut = in_range && lb > bound;
+        const bool keep = in_range && !cut;
+        const unsigned mk = __ballot_sync(0xffffffffu, keep), mc = __ballot_sync(0xffffffffu, cut);
+        if (lane == 0 && mc) atomicAdd(a.counters + 2, (unsigned long long)__popc(mc));
+        if (keep) {
+            QEntry e;
+            e.pr = pr;
+            e.Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+            e.seg = seg; e.base = base; e.n = n;
+            e.flags = (near ? 1u : 0u) | (((P.flags & kFlagStartIsOrigin) && unmoved) ? 2u : 0u);
+            e.pad = 0;
+            q[count + __popc(mk & lt)] = e;
+        }
+        __syncwarp();
+        count += __popc(mk);
+        if (count >= 32) drain(32);
+    }
+    if (count > 0) drain(count);
+}
+
 // ------------------------------------------------------------------------------------ leafwalk
 // One thread per leaf: decode the control sequence, walk H steps in registers in the start frame
 // (heading relative to the start heading, so sin.approx/cos.approx see |psi| <~ 1), score.
@@ -832,7 +922,13 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
     const bool head = a.cost_kind == 0;
     if (prefix) {
         const size_t sm = prefix_smem(a);
-        if (pass == 1 && a.prune)
+        if (pass == 1 && a.prune && a.g.S > kLeafChunk) {
+            // big grids (table streamed in chunks): warp-private survivor queues -- config 0: 2.6 s -> 0.25 s per tick
+            const size_t smq = sizeof(QEntry) * kWarpQueue * (kThreads / 32);
+            return head ? launch_persistent(prefix_pruned_kernel<true>, a, pass, smq, sms, st)
+                        : launch_persistent(prefix_pruned_kernel<false>, a, pass, smq, sms, st);
+        }
+        if (pass == 1 && a.prune)   // small grids: nodes are cut lane by lane (the queue costs more than it saves there)
             return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
                         : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
         if (pass == 1)
