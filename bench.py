@@ -363,7 +363,7 @@ def run_gpu(args):
                 bound="mufu", unit="Tops/s",
                 achieved=per_gpu_rate * mufu_a / 1e12, peak=mufu_peak / 1e12,
                 frac=per_gpu_rate * mufu_a / mufu_peak,
-                traffic=6806784,   # dram__bytes_read+write per launch, ncu --set full (profiles/r1e_cfg2_full.txt)
+                traffic=6802688,   # dram__bytes_read+write per launch, ncu --set full (profiles/r1g_cfg2_full.txt)
                 accounting="A: (2H+1) MUFU per rollout, one-thread-per-leaf design (SURVEY 8d); the prefix kernel "
                            "shares prefixes and executes 1.5 MUFU + 13.5 FP32 lane-ops (17 issue cycles) per rollout "
                            "(SASS of prefix_min_loop_far2), so frac>1 under A is expected",
