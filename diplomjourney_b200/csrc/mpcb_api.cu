@@ -487,7 +487,7 @@ static int solve_held_small(mpcb_handle *h, int cost_kind, int H, int64_t N, con
     if (threshold) a.threshold = put(threshold, (size_t)N);
     if (flags) {
         a.flags = d + (w - (double *)h->pin_in);
-        for (int64_t i = 0; i < N; ++i) *w++ = (flags[i] & MPCB_FLAG_SLOW) ? 1.0 : 0.0;
+        for (int64_t i = 0; i < N; ++i) *w++ = (double)(flags[i] & (MPCB_FLAG_SLOW | MPCB_FLAG_SKIP));
     }
     double *o = h->small_out.as<double>();
     a.out_cost = o; a.out_index = (long long *)(o + N); a.out_traj = o + 2 * N; a.out_ctl = o + 2 * N + 3 * (size_t)H * N;

@@ -209,7 +209,16 @@ __global__ void __launch_bounds__(kLoopThreads) held_small_kernel(const SmallArg
     cost.norm = sqrt(cost.A * cost.A + cost.B * cost.B);
     cost.theta = atan(cost.xt / cost.yt);
     cost.kind = a.cost_kind;
-    const bool slow = a.flags && (a.flags[n] != 0.0);
+    const int fl = a.flags ? (int)a.flags[n] : 0;
+    const bool slow = (fl & MPCB_FLAG_SLOW) != 0;
+    if (fl & MPCB_FLAG_SKIP) {                      // entry of a batch that is not to be solved
+        if (tid == 0) {
+            a.out_cost[n] = NAN; a.out_index[n] = -1;
+            for (int k = 0; k < 3 * a.H; ++k) a.out_traj[(size_t)n * 3 * a.H + k] = NAN;
+            a.out_ctl[2 * n] = NAN; a.out_ctl[2 * n + 1] = NAN;
+        }
+        return;
+    }
     for (int i = tid; i < a.nb; i += kLoopThreads) s_tan[i] = tan(a.beta[i]);
     __syncthreads();
     const double x0 = a.state[3 * n], y0 = a.state[3 * n + 1], phi0 = a.state[3 * n + 2];

@@ -148,7 +148,7 @@ struct FullLoopArgs {
 // one-launch float64 HELD solve from the raw grids (mpcb_loop.cu); all pointers are device
 struct SmallArgs {
     const double *v, *beta;            // raw grids
-    const double *state, *target, *origin, *threshold, *flags;   // flags as doubles (0 / non-0), nullable
+    const double *state, *target, *origin, *threshold, *flags;   // flags: MPCB_FLAG_* bits stored as doubles, nullable
     double *out_cost; long long *out_index; double *out_traj, *out_ctl;
     double L, delta_t, v_slow;
     int nv, nb, H, cost_kind;

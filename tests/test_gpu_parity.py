@@ -354,3 +354,21 @@ def test_large_heading_changes_stay_exact(solver):
         for i, s in enumerate(sc):
             _check(res, i, K.solve_full(s[:3], s[3:], s[:2], V, B, 4, C.COST_MM, L=Lshort), 4)
     solver.set_option("algo", nat.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("small_path", [1, 0])
+def test_skip_flag(solver, small_path):
+    """MPCB_FLAG_SKIP: entries of a batch that are not to be solved come back as (NaN, -1) on every path."""
+    V, B = C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0)
+    solver.set_grid(V, B, L, DT, VMIN)
+    solver.set_option("small_path", small_path)
+    sc = C.random_scenarios(4, 8)
+    flags = np.array([0, nat.FLAG_SKIP, nat.FLAG_SLOW, nat.FLAG_SKIP | nat.FLAG_SLOW], np.uint8)
+    r = solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, sc[:, :3], sc[:, 3:5], sc[:, :2], flags=flags)
+    solver.set_option("small_path", 1)
+    assert list(r["index"][[1, 3]]) == [-1, -1] and np.all(np.isnan(r["cost"][[1, 3]]))
+    for i, slow in ((0, False), (2, True)):
+        o = K.solve_held(sc[i, :3], sc[i, 3:5], sc[i, :2], V, B, 3, C.COST_TREE, slow=slow)
+        assert r["index"][i] == o["index"] and r["cost"][i] == pytest.approx(o["cost"], rel=1e-12)
+    full = solver.solve(nat.MODE_FULL, nat.COST_MM, 2, sc[:, :3], sc[:, 3:5], sc[:, :2], flags=flags)
+    assert list(full["index"][[1, 3]]) == [-1, -1] and full["index"][0] >= 0 and full["index"][2] >= 0
