@@ -153,3 +153,22 @@ def test_full_closed_loop_batch_matches_reference_ticks(golden):
                     k_rep += 1
                 elif t == 0 and tick["ret"][:2] == tick["state"][:2]:
                     k_rep += 1
+
+
+def test_integration_md_stub_runs_verbatim(golden):
+    """The ctypes stub printed in INTEGRATION.md section 2, executed as written (only the library path is filled in),
+    reproduces a reference HELD solve."""
+    import os
+    import re
+    from diplomjourney_b200 import _native, config
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(import ctypes as C.*?)```", md, re.S).group(1)
+    code = code.replace("/path/to/diplomjourney_b200/lib/libmpcb200.so", _native.library_path())
+    c = golden("held_single")["cases"][1]
+    ns = {k: getattr(config, k) for k in config.__all__}
+    ns.update(x_t=c["target"][0], y_t=c["target"][1], x_0=c["origin"][0], y_0=c["origin"][1])
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    cost, k, traj, ctl = ns["_gpu_held_solve"](c["state"], c["vector_v"], c["vector_beta"], c["slow"], 1e300)
+    assert k >= 0
+    np.testing.assert_allclose(list(traj[0]) + list(ctl), c["ret"], rtol=0, atol=1e-12)
