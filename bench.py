@@ -231,6 +231,8 @@ def run_gpu(args):
     solver.set_option("algo", {"auto": nat.ALGO_AUTO, "prefix": nat.ALGO_PREFIX, "leafwalk": nat.ALGO_LEAFWALK}[args.algo])
     # the headline evaluates EVERY leaf (as the reference does); the exact branch-and-bound is reported separately
     solver.set_option("prune", 0)
+    if args.nodes_per_thread:
+        solver.set_option("nodes_per_thread", args.nodes_per_thread)
 
     # each rank owns its own robots (contiguous ranges of the global batch): no data-path collective
     scen = C.random_scenarios(n * world, wl["seed"])[rank * n:(rank + 1) * n]
@@ -397,6 +399,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nodes-per-thread", type=int, default=0, choices=[0, 1, 2],
+                    help="prefix pass 1: depth-(H-1) nodes per thread (0 = library default)")
     ap.add_argument("--algo", default="auto", choices=["auto", "prefix", "leafwalk"],
                     help="expansion kernel: prefix (default for this workload) or the one-thread-per-leaf design")
     args = ap.parse_args()

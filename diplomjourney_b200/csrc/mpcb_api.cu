@@ -86,6 +86,7 @@ struct mpcb_handle_s {
     int algo = MPCB_ALGO_AUTO;
     int refine = 1;
     int small_path = 1;
+    int npt = 1;          // exhaustive prefix pass 1: nodes per thread
     int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
     DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub;
@@ -331,6 +332,10 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "refine")) h->refine = value != 0.0;
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
+    else if (!strcmp(name, "nodes_per_thread")) {
+        if (value != 1.0 && value != 2.0) return fail(h, MPCB_ERR_INVALID, "nodes_per_thread must be 1 or 2");
+        h->npt = (int)value;
+    }
     else return fail(h, MPCB_ERR_INVALID, "unknown option '%s'", name);
     return MPCB_OK;
 }
@@ -412,6 +417,7 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     a.tau = h->tau.as<double>();
     a.ub = h->ub.as<unsigned long long>();
     a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
+    a.npt = h->npt;
 
     int launches = 0;
     CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, (pl.prefix ? 1 : 0) | (mode == MPCB_MODE_HELD ? 2 : 0),

@@ -20,6 +20,9 @@
 //             tabulated displacement into the parent frame)
 #include "mpcb_types.cuh"
 
+#ifndef MPCB_UNROLL2
+#define MPCB_UNROLL2 4  // pairs per unrolled iteration of the two-node loop
+#endif
 #ifndef MPCB_UNROLL
 #define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (4..16 are within 1 %, profiles/r1b_variants.txt)
 #endif
@@ -330,6 +333,49 @@ __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__
     return best;
 }
 
+// two depth-(H-1) nodes per thread on the same table entry: the two LDS.128 of a leaf pair feed both nodes
+template <bool HEAD>
+__device__ __forceinline__ void prefix_min_loop_far2x2(const float4 *__restrict__ tab, int npairs, const ParentRegs &p0,
+                                                       const ParentRegs &p1, float &best0, float &best1) {
+    const float2 U0 = make_float2(p0.u2, p0.u2), W0 = make_float2(p0.w2, p0.w2);
+    const float2 D0 = make_float2(p0.D2, p0.D2), P0 = make_float2(p0.Dp, p0.Dp);
+    const float2 NU0 = make_float2(p0.nu, p0.nu), NW0 = make_float2(p0.nw, p0.nw);
+    const float2 E0 = make_float2(p0.e2, p0.e2), H0 = make_float2(-p0.h2, -p0.h2);
+    const float2 U1 = make_float2(p1.u2, p1.u2), W1 = make_float2(p1.w2, p1.w2);
+    const float2 D1 = make_float2(p1.D2, p1.D2), P1 = make_float2(p1.Dp, p1.Dp);
+    const float2 NU1 = make_float2(p1.nu, p1.nu), NW1 = make_float2(p1.nw, p1.nw);
+    const float2 E1 = make_float2(p1.e2, p1.e2), H1 = make_float2(-p1.h2, -p1.h2);
+    const float2 WD = make_float2(10000.0f, 10000.0f);
+    float b0 = best0, b1 = best1;
+    constexpr int kUnroll = MPCB_UNROLL2;
+#pragma unroll kUnroll
+    for (int m = 0; m < npairs; ++m) {
+        const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
+        const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
+        const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
+        const float2 num0 = __ffma2_rn(U0, A, __ffma2_rn(W0, B, R));
+        const float2 num1 = __ffma2_rn(U1, A, __ffma2_rn(W1, B, R));
+        const float2 dd0 = __fadd2_rn(D0, num0), dd1 = __fadd2_rn(D1, num1);
+        const float2 den0 = __fadd2_rn(make_float2(sqrt_approx(dd0.x), sqrt_approx(dd0.y)), P0);
+        const float2 den1 = __fadd2_rn(make_float2(sqrt_approx(dd1.x), sqrt_approx(dd1.y)), P1);
+        const float rp0 = rcp_approx(den0.x * den0.y), rp1 = rcp_approx(den1.x * den1.y);
+        const float2 tt0 = __fmul2_rn(num0, __fmul2_rn(make_float2(rp0, rp0), make_float2(den0.y, den0.x)));
+        const float2 tt1 = __fmul2_rn(num1, __fmul2_rn(make_float2(rp1, rp1), make_float2(den1.y, den1.x)));
+        const float2 q0 = __ffma2_rn(NU0, A, __fmul2_rn(NW0, B));
+        const float2 q1 = __ffma2_rn(NU1, A, __fmul2_rn(NW1, B));
+        float2 acc0 = __fmul2_rn(q0, __fadd2_rn(E0, q0));
+        float2 acc1 = __fmul2_rn(q1, __fadd2_rn(E1, q1));
+        if (HEAD) {
+            acc0 = __ffma2_rn(G, __fadd2_rn(G, H0), acc0);
+            acc1 = __ffma2_rn(G, __fadd2_rn(G, H1), acc1);
+        }
+        const float2 L0 = __ffma2_rn(WD, tt0, acc0), L1 = __ffma2_rn(WD, tt1, acc1);
+        b0 = fminf(b0, fminf(L0.x, L0.y));
+        b1 = fminf(b1, fminf(L1.x, L1.y));
+    }
+    best0 = b0; best1 = b1;
+}
+
 // scalar flavour on the same pair table: NEAR regime, or a node sitting exactly on the line origin
 template <bool HEAD>
 __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
@@ -460,6 +506,75 @@ prefix_kernel(const LaunchArgs a) {
         }
         if (PASS == 1) publish_segmin(a, seg, segbest);
         else publish_best(a, n, bJ, bj, s_J, s_j);
+    }
+}
+
+// ------------------------------------------------------------------------------------ prefix, two nodes per thread
+// Pass 1, exhaustive only (option "nodes_per_thread" = 2): a 512-thread CTA covers the same four 256-node tiles as
+// prefix_kernel<1>, thread t holding node t and node t + 512 of the work item.  Same arithmetic per node, so the
+// segment minima (and everything downstream) are bit-identical to the one-node kernel.
+template <bool HEAD>
+__global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const LaunchArgs a) {
+    extern __shared__ float4 s_leaf[];
+    const int tid = threadIdx.x;
+    const int S = a.g.S;
+    const bool single = S <= kLeafChunk;
+    const float4 *__restrict__ gtab = a.g.leaf32p;
+    auto chunk_f4 = [&](int cn) { return 2 * ((cn + 1) >> 1); };
+    if (single) {
+        for (int i = tid; i < chunk_f4(S); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
+        __syncthreads();
+    }
+    constexpr unsigned groups = kPrefixCta / kThreads;
+    const unsigned long long qps = (a.tiles_per_solve + groups - 1) / groups;
+    const unsigned long long nwork = (unsigned long long)a.N * qps;
+    for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const long long n = (long long)(w / qps);
+        const unsigned long long tile0 = (w - (unsigned long long)n * qps) * groups;
+        const SolveParams &P = a.sp[n];
+        if (P.flags & kFlagSkip) continue;
+        const bool origin_case = (P.flags & kFlagStartIsOrigin) != 0;
+        ParentRegs pr[2] = {};
+        bool near[2], special[2], active[2];
+        double base[2];
+        float best[2], Lspecial[2];
+        unsigned seg[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const unsigned node = tid + k * (kPrefixCta / 2);
+            const unsigned long long tile = tile0 + node / kThreads;
+            const unsigned long long p = a.u_begin + tile * kThreads + (node % kThreads);
+            active[k] = tile < a.tiles_per_solve && p < a.u_end;
+            seg[k] = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
+            bool unmoved = false;
+            near[k] = false; base[k] = 0.0; best[k] = INFINITY;
+            if (active[k]) base[k] = parent_setup(a, P, p, pr[k], near[k], unmoved, nullptr);
+            special[k] = active[k] && origin_case && unmoved;
+            Lspecial[k] = (float)(P.special - 0.25 * (double)pr[k].e2 * (double)pr[k].e2);
+        }
+        const bool both = active[0] && active[1] && !near[0] && !near[1] && !special[0] && !special[1];
+        for (int c0 = 0; c0 < S; c0 += kLeafChunk) {
+            const int cn = min(kLeafChunk, S - c0);
+            if (!single) {
+                __syncthreads();
+                for (int i = tid; i < chunk_f4(cn); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
+                __syncthreads();
+            }
+            const int npairs = (cn + 1) >> 1;
+            if (both) {
+                prefix_min_loop_far2x2<HEAD>(s_leaf, npairs, pr[0], pr[1], best[0], best[1]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!active[k]) continue;
+                    best[k] = (near[k] || special[k])
+                                  ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr[k], near[k], special[k], Lspecial[k], best[k])
+                                  : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr[k], best[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) publish_segmin(a, seg[k], active[k] ? base[k] + (double)best[k] : INFINITY);
     }
 }
 
@@ -931,6 +1046,9 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
         if (pass == 1 && a.prune)   // small grids: nodes are cut lane by lane (the queue costs more than it saves there)
             return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
                         : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
+        if (pass == 1 && a.npt == 2)
+            return head ? launch_persistent(prefix2_kernel<true>, a, pass, sm, sms, st, kPrefixCta / 2)
+                        : launch_persistent(prefix2_kernel<false>, a, pass, sm, sms, st, kPrefixCta / 2);
         if (pass == 1)
             return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixCta)
                         : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixCta);

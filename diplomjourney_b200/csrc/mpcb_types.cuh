@@ -114,6 +114,7 @@ struct LaunchArgs {
     unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
+    int npt;                               // depth-(H-1) nodes per thread in the exhaustive prefix pass 1 (1 or 2)
     int i0_begin, i0_end;                   // first-control range of this launch (probe)
     const double *tau;                     // [N] J_rel window upper edge
     // dump

@@ -372,3 +372,32 @@ def test_skip_flag(solver, small_path):
         assert r["index"][i] == o["index"] and r["cost"][i] == pytest.approx(o["cost"], rel=1e-12)
     full = solver.solve(nat.MODE_FULL, nat.COST_MM, 2, sc[:, :3], sc[:, 3:5], sc[:, :2], flags=flags)
     assert list(full["index"][[1, 3]]) == [-1, -1] and full["index"][0] >= 0 and full["index"][2] >= 0
+
+
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_two_nodes_per_thread_is_bit_identical(solver, cost):
+    """option nodes_per_thread=2 (exhaustive prefix pass 1 with two depth-(H-1) nodes per thread) does the same
+    arithmetic per node: identical results to nodes_per_thread=1 and to the oracle, including ragged last tiles,
+    a robot on the line origin, a robot next to its target (NEAR regime) and a chunked table (S > 1024)."""
+    grids = [(np.linspace(0.0, 1.0, 11), np.linspace(-1.0, 1.0, 13), 3, 6),        # 143^2 nodes: ragged tiles
+             (C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0), 3, 4),
+             (np.linspace(0.1, 1.0, 30), np.linspace(-1.0, 1.0, 41), 2, 5)]        # S = 1230: two table chunks
+    solver.set_option("algo", nat.ALGO_PREFIX)
+    solver.set_option("prune", 0)
+    try:
+        for V, B, H, n in grids:
+            solver.set_grid(V, B, L, DT, VMIN)
+            sc = C.random_scenarios(n, 900 + H)
+            sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]
+            solver.set_option("nodes_per_thread", 1)
+            one = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
+            solver.set_option("nodes_per_thread", 2)
+            two = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
+            for k in ("index", "cost", "traj", "first_control"):
+                np.testing.assert_array_equal(two[k], one[k])
+            for i, s in enumerate(sc):
+                _check(two, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, cost), H)
+    finally:
+        solver.set_option("nodes_per_thread", 1)
+        solver.set_option("prune", 1)
+        solver.set_option("algo", nat.ALGO_AUTO)
