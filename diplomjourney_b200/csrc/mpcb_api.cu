@@ -86,7 +86,8 @@ struct mpcb_handle_s {
     int algo = MPCB_ALGO_AUTO;
     int refine = 1;
     int small_path = 1;
-    int npt = 1;          // exhaustive prefix pass 1: nodes per thread
+    int dump_direct = 0;  // mpcb_dump_leaves_host, prefix: dump the values pass 1 ranks with
+    int npt = 2;          // exhaustive prefix pass 1: nodes per thread (2: +6 %, tools/ubench)
     int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
     DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub;
@@ -172,6 +173,7 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
     memset(&a, 0, sizeof a);
     a.g = h->g;
     a.mode = mode; a.H = H; a.cost_kind = cost_kind; a.refine = h->refine;
+    a.dump_direct = h->dump_direct; a.npt = h->npt;
     a.N = N;
     unsigned long long S = (unsigned long long)h->g.S, pw = 1;
     a.idx32 = (!pl.prefix && pl.u_end < (1ULL << 32)) ? 1 : 0;
@@ -332,6 +334,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "refine")) h->refine = value != 0.0;
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
+    else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
     else if (!strcmp(name, "nodes_per_thread")) {
         if (value != 1.0 && value != 2.0) return fail(h, MPCB_ERR_INVALID, "nodes_per_thread must be 1 or 2");
         h->npt = (int)value;

@@ -77,6 +77,7 @@ struct ParentRegs {
     float D2, Dp;      // |target|^2, |target|
     float nu, nw;      // wl * unit normal of the tracked line, parent frame
     float e2, h2;      // 2 * wl*signed line distance of the parent, 2 * wh*(theta - phi_parent)
+    float kc, eh, nhh; // direct form (prefix pass 1): float(-kWd |target|), e2/2, -h2/2
 };
 
 // fp32 leaf part L of the cost: J_leaf = Kbase + base_parent + L,
@@ -99,6 +100,22 @@ __device__ __forceinline__ float leaf_val(float a, float b, float r, float g, co
     float acc = q * (p.e2 + q);
     if (HEAD) acc = __fmaf_rn(g, g - p.h2, acc);
     return __fmaf_rn(10000.0f, t, acc);
+}
+
+// DIRECT form of the same leaf part (prefix pass 1, FAR regime), 9.5 FP32 ops + 1 MUFU per leaf instead of 14 + 1.5:
+//   L' = [kWd sqrt(D2 + num) + kc] + (q + eh)^2 + (g + nhh)^2,   kc = float(-kWd Dp), eh = e2/2, nhh = -h2/2
+// i.e. L' = L + (kWd Dp + kc) + eh^2 + nhh^2 in exact arithmetic; the node's base absorbs that constant in float64
+// (parent_setup's base_direct).  The distance term now carries the rounding of d itself (~2^-22 d kWd), so this
+// form only RANKS leaves for pass 1 with its own, wider error bound tol1 (prep_kernel); pass 2 filters with leaf_val.
+template <bool HEAD>
+__device__ __forceinline__ float leaf_val_direct(float a, float b, float r, float g, const ParentRegs &p) {
+    const float num = __fmaf_rn(p.u2, a, __fmaf_rn(p.w2, b, r));
+    const float s = sqrt_approx(p.D2 + num);
+    const float t = __fmaf_rn(10000.0f, s, p.kc);
+    const float q = __fmaf_rn(p.nu, a, __fmaf_rn(p.nw, b, p.eh));
+    float acc = __fmaf_rn(q, q, t);
+    if (HEAD) { const float gg = g + p.nhh; acc = __fmaf_rn(gg, gg, acc); }
+    return acc;
 }
 
 // returns the remainder term -kWd (Dp - float(Dp)) that a NEAR parent adds to its base
@@ -129,7 +146,7 @@ __device__ __forceinline__ double quad_min(double e, double Q) {
 
 __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
                                                unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved,
-                                               double *lower_bound = nullptr) {
+                                               double *lower_bound = nullptr, double *base_direct = nullptr) {
     double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
     unsigned long long rem = p;
     const int D = a.H - 1;
@@ -161,6 +178,10 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     const double base0 = kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
     // no child can do better than: one step straight at the target (d >= Dp - s_max, triangle inequality)
     // plus the most favourable line and heading offsets  (|q| <= wl s_max, |g| <= wh dphi_max)
+    if (base_direct) {
+        pr.kc = (float)(-kWd * Dp); pr.eh = 0.5f * pr.e2; pr.nhh = -0.5f * pr.h2;
+        *base_direct = base0 + (-kWd * Dp - (double)pr.kc) - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
+    }
     if (lower_bound)
         *lower_bound = base0 - kWd * a.g.smax + quad_min(2.0 * ep, P.wl * a.g.smax) + quad_min(-2.0 * hp, P.wh * a.g.dphimax);
     return base0 + (near ? dp_rem : 0.0);
@@ -308,9 +329,9 @@ template <bool HEAD>
 __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
                                                       float best) {
     const float2 U2 = make_float2(pr.u2, pr.u2), W2 = make_float2(pr.w2, pr.w2);
-    const float2 D2 = make_float2(pr.D2, pr.D2), DP = make_float2(pr.Dp, pr.Dp);
+    const float2 D2 = make_float2(pr.D2, pr.D2), KC = make_float2(pr.kc, pr.kc);
     const float2 NU = make_float2(pr.nu, pr.nu), NW = make_float2(pr.nw, pr.nw);
-    const float2 E2 = make_float2(pr.e2, pr.e2), NH2 = make_float2(-pr.h2, -pr.h2);
+    const float2 EH = make_float2(pr.eh, pr.eh), NHH = make_float2(pr.nhh, pr.nhh);
     const float2 WD = make_float2(10000.0f, 10000.0f);
     constexpr int kUnroll = MPCB_UNROLL;
 #pragma unroll kUnroll
@@ -318,17 +339,13 @@ __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__
         const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
         const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
         const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
-        const float2 num = __ffma2_rn(U2, A, __ffma2_rn(W2, B, R));
-        const float2 dd = __fadd2_rn(D2, num);
-        const float2 den = __fadd2_rn(make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)), DP);
-        // both reciprocals of the pair from ONE MUFU.RCP (Montgomery): 1/y0 = y1/(y0 y1), 1/y1 = y0/(y0 y1)
-        const float rp = rcp_approx(den.x * den.y);
-        const float2 t = __fmul2_rn(num, __fmul2_rn(make_float2(rp, rp), make_float2(den.y, den.x)));
-        const float2 q = __ffma2_rn(NU, A, __fmul2_rn(NW, B));
-        float2 acc = __fmul2_rn(q, __fadd2_rn(E2, q));
-        if (HEAD) acc = __ffma2_rn(G, __fadd2_rn(G, NH2), acc);
-        const float2 L = __ffma2_rn(WD, t, acc);
-        best = fminf(best, fminf(L.x, L.y));
+        // leaf_val_direct on two leaves at a time
+        const float2 dd = __fadd2_rn(D2, __ffma2_rn(U2, A, __ffma2_rn(W2, B, R)));
+        const float2 t = __ffma2_rn(WD, make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)), KC);
+        const float2 q = __ffma2_rn(NU, A, __ffma2_rn(NW, B, EH));
+        float2 acc = __ffma2_rn(q, q, t);
+        if (HEAD) { const float2 gg = __fadd2_rn(G, NHH); acc = __ffma2_rn(gg, gg, acc); }
+        best = fminf(best, fminf(acc.x, acc.y));
     }
     return best;
 }
@@ -338,13 +355,13 @@ template <bool HEAD>
 __device__ __forceinline__ void prefix_min_loop_far2x2(const float4 *__restrict__ tab, int npairs, const ParentRegs &p0,
                                                        const ParentRegs &p1, float &best0, float &best1) {
     const float2 U0 = make_float2(p0.u2, p0.u2), W0 = make_float2(p0.w2, p0.w2);
-    const float2 D0 = make_float2(p0.D2, p0.D2), P0 = make_float2(p0.Dp, p0.Dp);
+    const float2 D0 = make_float2(p0.D2, p0.D2), K0 = make_float2(p0.kc, p0.kc);
     const float2 NU0 = make_float2(p0.nu, p0.nu), NW0 = make_float2(p0.nw, p0.nw);
-    const float2 E0 = make_float2(p0.e2, p0.e2), H0 = make_float2(-p0.h2, -p0.h2);
+    const float2 E0 = make_float2(p0.eh, p0.eh), H0 = make_float2(p0.nhh, p0.nhh);
     const float2 U1 = make_float2(p1.u2, p1.u2), W1 = make_float2(p1.w2, p1.w2);
-    const float2 D1 = make_float2(p1.D2, p1.D2), P1 = make_float2(p1.Dp, p1.Dp);
+    const float2 D1 = make_float2(p1.D2, p1.D2), K1 = make_float2(p1.kc, p1.kc);
     const float2 NU1 = make_float2(p1.nu, p1.nu), NW1 = make_float2(p1.nw, p1.nw);
-    const float2 E1 = make_float2(p1.e2, p1.e2), H1 = make_float2(-p1.h2, -p1.h2);
+    const float2 E1 = make_float2(p1.eh, p1.eh), H1 = make_float2(p1.nhh, p1.nhh);
     const float2 WD = make_float2(10000.0f, 10000.0f);
     float b0 = best0, b1 = best1;
     constexpr int kUnroll = MPCB_UNROLL2;
@@ -353,25 +370,20 @@ __device__ __forceinline__ void prefix_min_loop_far2x2(const float4 *__restrict_
         const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
         const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
         const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
-        const float2 num0 = __ffma2_rn(U0, A, __ffma2_rn(W0, B, R));
-        const float2 num1 = __ffma2_rn(U1, A, __ffma2_rn(W1, B, R));
-        const float2 dd0 = __fadd2_rn(D0, num0), dd1 = __fadd2_rn(D1, num1);
-        const float2 den0 = __fadd2_rn(make_float2(sqrt_approx(dd0.x), sqrt_approx(dd0.y)), P0);
-        const float2 den1 = __fadd2_rn(make_float2(sqrt_approx(dd1.x), sqrt_approx(dd1.y)), P1);
-        const float rp0 = rcp_approx(den0.x * den0.y), rp1 = rcp_approx(den1.x * den1.y);
-        const float2 tt0 = __fmul2_rn(num0, __fmul2_rn(make_float2(rp0, rp0), make_float2(den0.y, den0.x)));
-        const float2 tt1 = __fmul2_rn(num1, __fmul2_rn(make_float2(rp1, rp1), make_float2(den1.y, den1.x)));
-        const float2 q0 = __ffma2_rn(NU0, A, __fmul2_rn(NW0, B));
-        const float2 q1 = __ffma2_rn(NU1, A, __fmul2_rn(NW1, B));
-        float2 acc0 = __fmul2_rn(q0, __fadd2_rn(E0, q0));
-        float2 acc1 = __fmul2_rn(q1, __fadd2_rn(E1, q1));
+        const float2 dd0 = __fadd2_rn(D0, __ffma2_rn(U0, A, __ffma2_rn(W0, B, R)));
+        const float2 dd1 = __fadd2_rn(D1, __ffma2_rn(U1, A, __ffma2_rn(W1, B, R)));
+        const float2 tt0 = __ffma2_rn(WD, make_float2(sqrt_approx(dd0.x), sqrt_approx(dd0.y)), K0);
+        const float2 tt1 = __ffma2_rn(WD, make_float2(sqrt_approx(dd1.x), sqrt_approx(dd1.y)), K1);
+        const float2 q0 = __ffma2_rn(NU0, A, __ffma2_rn(NW0, B, E0));
+        const float2 q1 = __ffma2_rn(NU1, A, __ffma2_rn(NW1, B, E1));
+        float2 acc0 = __ffma2_rn(q0, q0, tt0), acc1 = __ffma2_rn(q1, q1, tt1);
         if (HEAD) {
-            acc0 = __ffma2_rn(G, __fadd2_rn(G, H0), acc0);
-            acc1 = __ffma2_rn(G, __fadd2_rn(G, H1), acc1);
+            const float2 g0 = __fadd2_rn(G, H0), g1 = __fadd2_rn(G, H1);
+            acc0 = __ffma2_rn(g0, g0, acc0);
+            acc1 = __ffma2_rn(g1, g1, acc1);
         }
-        const float2 L0 = __ffma2_rn(WD, tt0, acc0), L1 = __ffma2_rn(WD, tt1, acc1);
-        b0 = fminf(b0, fminf(L0.x, L0.y));
-        b1 = fminf(b1, fminf(L1.x, L1.y));
+        b0 = fminf(b0, fminf(acc0.x, acc0.y));
+        b1 = fminf(b1, fminf(acc1.x, acc1.y));
     }
     best0 = b0; best1 = b1;
 }
@@ -444,18 +456,19 @@ prefix_kernel(const LaunchArgs a) {
             const bool in_range = tile < tile_hi && p < a.u_end;
             ParentRegs pr = {};
             bool near = false, unmoved = false;
-            double base = 0.0, lb = -INFINITY;
+            double base = 0.0, base_direct = 0.0, lb = -INFINITY;
             bool active = in_range;
-            if (active) base = parent_setup(a, P, p, pr, near, unmoved, &lb);
+            if (active) base = parent_setup(a, P, p, pr, near, unmoved, &lb, PASS == 1 ? &base_direct : nullptr);
             if (PASS == 2 && a.prune && active && lb > tau + P.tol) active = false;   // cannot hold an in-window leaf
             if (PASS == 1 && PRUNE) {
-                const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + 2.0 * P.tol;
+                const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
                 const bool cut = active && lb > bound;
                 const unsigned m = __ballot_sync(0xffffffffu, cut);
                 if ((tid & 31) == 0 && m) atomicAdd(a.counters + 2, (unsigned long long)__popc(m));
                 active = active && !cut;
             }
             const bool special = active && origin_case && unmoved;
+            if (PASS == 1 && !(near || special)) base = base_direct;   // the packed loop ranks in the direct form
             double ex = 0.0, ey = 0.0, ephi = 0.0;
             bool have_pose = false;
             float best = INFINITY;
@@ -501,7 +514,7 @@ prefix_kernel(const LaunchArgs a) {
             if (PASS == 1 && PRUNE) {
                 // tighten the solve's upper bound: this tile's best fp32 value + its error bound is >= a true leaf cost
                 const double v = warp_min(active ? base + (double)best : INFINITY);
-                if ((tid & 31) == 0 && v < INFINITY) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol));
+                if ((tid & 31) == 0 && v < INFINITY) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol1));
             }
         }
         if (PASS == 1) publish_segmin(a, seg, segbest);
@@ -548,8 +561,10 @@ __global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const Launch
             seg[k] = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
             bool unmoved = false;
             near[k] = false; base[k] = 0.0; best[k] = INFINITY;
-            if (active[k]) base[k] = parent_setup(a, P, p, pr[k], near[k], unmoved, nullptr);
+            double base_direct = 0.0;
+            if (active[k]) base[k] = parent_setup(a, P, p, pr[k], near[k], unmoved, nullptr, &base_direct);
             special[k] = active[k] && origin_case && unmoved;
+            if (!(near[k] || special[k])) base[k] = base_direct;
             Lspecial[k] = (float)(P.special - 0.25 * (double)pr[k].e2 * (double)pr[k].e2);
         }
         const bool both = active[0] && active[1] && !near[0] && !near[1] && !special[0] && !special[1];
@@ -617,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
             if (v < INFINITY) {
                 atomicMin(reinterpret_cast<unsigned long long *>(a.segmin) + e.seg, ordered_key(v));
                 // this node's best fp32 value + its error bound is >= a true leaf cost: tighten the upper bound
-                atomicMin(a.ub + e.n, ordered_key(v + 0.5 * a.sp[e.n].tol));
+                atomicMin(a.ub + e.n, ordered_key(v + 0.5 * a.sp[e.n].tol1));
             }
         }
         __syncwarp();
@@ -645,9 +660,9 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
         const bool in_range = p < a.u_end;
         ParentRegs pr = {};
         bool near = false, unmoved = false;
-        double base = 0.0, lb = -INFINITY;
-        if (in_range) base = parent_setup(a, P, p, pr, near, unmoved, &lb);
-        const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + 2.0 * P.tol;
+        double base = 0.0, base_direct = 0.0, lb = -INFINITY;
+        if (in_range) base = parent_setup(a, P, p, pr, near, unmoved, &lb, &base_direct);
+        const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
         const bool cut = in_range && lb > bound;
         const bool keep = in_range && !cut;
         const unsigned mk = __ballot_sync(0xffffffffu, keep), mc = __ballot_sync(0xffffffffu, cut);
@@ -656,8 +671,9 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
             QEntry e;
             e.pr = pr;
             e.Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
-            e.seg = seg; e.base = base; e.n = n;
+            e.seg = seg; e.n = n;
             e.flags = (near ? 1u : 0u) | (((P.flags & kFlagStartIsOrigin) && unmoved) ? 2u : 0u);
+            e.base = e.flags ? base : base_direct;
             e.pad = 0;
             q[count + __popc(mk & lt)] = e;
         }
@@ -844,15 +860,19 @@ __global__ void __launch_bounds__(kThreads) prefix_dump_kernel(const LaunchArgs 
          p += (unsigned long long)gridDim.x * kThreads) {
         ParentRegs pr;
         bool near, unmoved;
-        const double base = parent_setup(a, P, p, pr, near, unmoved);
+        double base_direct;
+        double base = parent_setup(a, P, p, pr, near, unmoved, nullptr, &base_direct);
         const bool special = (P.flags & kFlagStartIsOrigin) && unmoved;
         const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+        const bool direct = a.dump_direct && !near && !special;      // what pass 1 ranks this node's children with
+        if (direct) base = base_direct;
         for (int c = 0; c < S; ++c) {
             const unsigned long long j = p * S + c;
             if (j < a.dump_begin || j >= a.dump_begin + a.dump_count) continue;
             float4 t = __ldg(a.g.leaf32 + c);
-            float L = near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
-                           : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
+            float L = direct ? leaf_val_direct<HEAD>(t.x, t.y, t.z, t.w, pr)
+                      : near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
+                             : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
             if (special && t.z == 0.f) L = Lspecial;
             jrel[j - a.dump_begin] = base + (double)L;
         }
@@ -907,6 +927,17 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     // sin.approx / cos.approx: absolute error 2^-21.4 on [-pi, pi], growing with the argument beyond it
     if (!prefix) M += kWd * Rtot * 8.0 * fmax(1.0, H * dphimax / 3.141592653589793);
     P.tol = 2.0 * M * 1.1920928955078125e-07 * tol_scale;
+    P.tol1 = P.tol;
+    if (prefix) {
+        // direct form of the prefix pass 1 (leaf_val_direct), in units of 2^-23:
+        //   distance   kWd d (sqrt.approx 1 + roundings of D2, num, the sum ~0.75)        -> 3 kWd Dmax
+        //   kWd s + kc rounded at magnitude <= kWd smax, table/u2/w2 roundings             -> 2 kWd smax
+        //   (q + eh)^2 with |q + eh| <= E1: 1.5 ulp on the sum, squared, + the add         -> 4 E1^2
+        //   (g + nhh)^2 with |g + nhh| <= H1                                               -> 3 H1^2
+        const double Dmax = P.d0 + Rtot, E1 = E + Q, H1 = Hh + Gl;
+        const double M1 = 3.0 * kWd * Dmax + 2.0 * kWd * smax + 4.0 * E1 * E1 + 3.0 * H1 * H1;
+        P.tol1 = fmax(P.tol, 2.0 * M1 * 1.1920928955078125e-07 * tol_scale);
+    }
     P.flags = f; P.pad = 0;
     out[n] = P;
 }
@@ -951,9 +982,9 @@ __global__ void __launch_bounds__(kThreads) reduce_compact_kernel(const LaunchAr
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int i = 1; i < kThreads / 32; ++i) v = fmin(v, s_J[i]);
-            const double t = v + (a.refine ? a.sp[n].tol : 0.0);
-            s_tau = t;
-            tau[n] = t;
+            // the segment holding the true argmin has a pass-1 minimum <= v + tol1; its pass-2 value is <= v + (tol1+tol)/2
+            s_tau = v + a.sp[n].tol1;
+            tau[n] = v + 0.5 * (a.sp[n].tol1 + a.sp[n].tol);
             a.bestJ[n] = INFINITY;
             a.bestIdx[n] = -1;
             a.lock[n] = 0;

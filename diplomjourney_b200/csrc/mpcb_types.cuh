@@ -83,7 +83,8 @@ struct __align__(16) SolveParams {
     double hp0;                 // wh * (theta - phi0)
     double wl, wh;              // sqrt of the line / heading weights
     double Kbase;               // kWd d0 + e0^2 + hp0^2 (cost terms of the start pose): J = Kbase + J_rel
-    double tol;                 // half-width of the candidate window of the refinement pass
+    double tol;                 // 2 x error bound of the fp32 leaf value that pass 2 filters with (leaf_val / leafwalk)
+    double tol1;                // 2 x error bound of the value pass 1 RANKS with (prefix: direct form; else = tol)
     double special;             // 1e6 * wl^2: squared line term of the "on the origin" special case
     int flags;                  // bit0 slow, bit1 start_is_origin, bit2 near (leafwalk regime)
     int pad;
@@ -114,6 +115,7 @@ struct LaunchArgs {
     unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
+    int dump_direct;                       // prefix dump: direct (pass-1) form instead of the pass-2 form
     int npt;                               // depth-(H-1) nodes per thread in the exhaustive prefix pass 1 (1 or 2)
     int i0_begin, i0_end;                   // first-control range of this launch (probe)
     const double *tau;                     // [N] J_rel window upper edge

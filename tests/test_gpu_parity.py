@@ -249,8 +249,9 @@ def test_config0_default_full_tree_subtrees(solver):
         np.testing.assert_allclose(r["traj"][0], o["traj"], rtol=0, atol=1e-12)
 
 
-def _eps_model(s, origin, H, cost, prefix, smax, dphimax):
-    """Python mirror of the error window prep_kernel computes (tol/2)."""
+def _eps_model(s, origin, H, cost, prefix, smax, dphimax, direct=False):
+    """Python mirror of the error bounds prep_kernel computes: tol/2 (the value pass 2 filters with), or with
+    ``direct`` tol1/2 (the cheaper direct form the prefix pass 1 ranks with)."""
     xs, ys, p0, xt, yt = s
     wl, wh = (10.0, math.sqrt(10.0)) if cost == C.COST_MM else (100.0, 0.0)
     A, Bc, Cc = yt - origin[1], xt - origin[0], xt * origin[1] - yt * origin[0]
@@ -264,14 +265,23 @@ def _eps_model(s, origin, H, cost, prefix, smax, dphimax):
     M = 1e4 * Rl * 16 + 4 * Q * (2 * E + Q) + 4 * Gl * (Gl + 2 * Hh)
     if not prefix:
         M += 1e4 * Rtot * 8 * max(1.0, H * dphimax / math.pi)
+    if direct:
+        d0 = math.hypot(xt - xs, yt - ys)
+        M1 = 3 * 1e4 * (d0 + Rtot) + 2 * 1e4 * smax + 4 * (E + Q) ** 2 + 3 * (Hh + Gl) ** 2
+        M = max(M, M1)
     return M * 2.0 ** -23
 
 
-@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX, "prefix_direct"])
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
 def test_fp32_stage_error_stays_inside_the_refinement_window(solver, algo, cost):
     """Every leaf of many small trees (far / near the target / far off the tracked line): the fp32 value the
-    kernels compare lies within the per-solve window half-width eps that the refinement pass assumes."""
+    kernels compare lies within the per-solve window half-width eps that the refinement pass assumes.
+    "prefix_direct" dumps the values the prefix pass 1 RANKS with (leaf_val_direct) against their own bound tol1/2."""
+    direct = algo == "prefix_direct"
+    if direct:
+        algo = nat.ALGO_PREFIX
+    solver.set_option("dump_direct", 1 if direct else 0)
     V, B = [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 9)
     solver.set_grid(V, B, L, DT, VMIN)
     vv, bb, dphi = C.control_tables(V, B, L, DT)
@@ -288,8 +298,9 @@ def test_fp32_stage_error_stays_inside_the_refinement_window(solver, algo, cost)
         _, J = solver.dump_leaves(nat.MODE_FULL, COSTS[cost], H, s[:3], s[3:5], origin, algo=algo)
         Jo = C.full_leaf_costs(s[:3], s[3:5], origin, V, B, H, cost)
         ok = Jo < 1e7
-        eps = _eps_model(s, origin, H, cost, algo == nat.ALGO_PREFIX, smax, dphimax)
+        eps = _eps_model(s, origin, H, cost, algo == nat.ALGO_PREFIX, smax, dphimax, direct)
         worst_ratio = max(worst_ratio, float(np.abs(J - Jo)[ok].max() / eps))
+    solver.set_option("dump_direct", 0)
     assert worst_ratio < 1.0, worst_ratio
 
 
@@ -398,6 +409,6 @@ def test_two_nodes_per_thread_is_bit_identical(solver, cost):
             for i, s in enumerate(sc):
                 _check(two, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, cost), H)
     finally:
-        solver.set_option("nodes_per_thread", 1)
+        solver.set_option("nodes_per_thread", 2)                       # library default
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
