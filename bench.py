@@ -354,7 +354,7 @@ def run_gpu(args):
         fp32_peak = SM_COUNT * FP32_PER_CLK_SM * clk_hz
         per_gpu_rate = leaves_per_solve * n / (kern_ms * 1e-3)           # rollouts/s of one GPU, per step
         mufu_a = 2 * Hh + 1                                              # accounting A
-        issue_cyc = 11.5 if args.nodes_per_thread == 1 else 11.0         # issue cycles per rollout of the pair loop
+        issue_cyc = 10.5 if args.nodes_per_thread == 1 else 10.0         # issue cycles per rollout of the pair loop
         line = dict(
             metric="candidate rollouts/s (MPC inner loop)", value=value, unit="rollouts/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
@@ -366,13 +366,13 @@ def run_gpu(args):
                 bound="mufu", unit="Tops/s",
                 achieved=per_gpu_rate * mufu_a / 1e12, peak=mufu_peak / 1e12,
                 frac=per_gpu_rate * mufu_a / mufu_peak,
-                traffic=6802688,   # dram__bytes_read+write per launch, ncu --set full (profiles/r1g_cfg2_full.txt)
+                traffic=6802688,   # dram__bytes_read+write per launch, ncu --set full (profiles/r1h_cfg2_full.txt)
                 accounting="A: (2H+1) MUFU per rollout, one-thread-per-leaf design (SURVEY 8d); the prefix kernel "
-                           "shares prefixes and executes 1 MUFU + 9.5 FP32 lane-ops per rollout (SASS of "
-                           "prefix_min_loop_far2x2: per leaf pair and node 9 packed f32x2 ops at 2 issue cycles, "
+                           "shares prefixes and executes 1 MUFU + 8.5 FP32 lane-ops per rollout (SASS of "
+                           "prefix_min_loop_far2x2: per leaf pair and node 7 FFMA2 + 1 FADD2 at 2 issue cycles each, "
                            "2 MUFU.SQRT, 1 FMNMX3, 2 LDS.128 shared by the thread's nodes), so frac>1 under A is expected",
-                executed=dict(mufu_per_rollout=1.0, fp32_ops_per_rollout=9.5, issue_cycles_per_rollout=issue_cyc,
-                              mufu_frac=per_gpu_rate * 1.0 / mufu_peak, fp32_frac=per_gpu_rate * 9.5 / fp32_peak,
+                executed=dict(mufu_per_rollout=1.0, fp32_ops_per_rollout=8.5, issue_cycles_per_rollout=issue_cyc,
+                              mufu_frac=per_gpu_rate * 1.0 / mufu_peak, fp32_frac=per_gpu_rate * 8.5 / fp32_peak,
                               issue_frac=per_gpu_rate * issue_cyc / fp32_peak),
                 hbm_gbs=(h2d + d2h) / (kern_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
                 peak_src=f"{pk['src']} sm_max_mhz={pk['sm_max_mhz']:.0f} x {SM_COUNT} SMs x {MUFU_PER_CLK_SM} MUFU/clk/SM",

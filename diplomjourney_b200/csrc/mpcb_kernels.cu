@@ -77,7 +77,8 @@ struct ParentRegs {
     float D2, Dp;      // |target|^2, |target|
     float nu, nw;      // wl * unit normal of the tracked line, parent frame
     float e2, h2;      // 2 * wl*signed line distance of the parent, 2 * wh*(theta - phi_parent)
-    float kc, eh, nhh; // direct form (prefix pass 1): float(-kWd |target|), e2/2, -h2/2
+    float eh, nhh;     // direct form (prefix pass 1): e2/2, -h2/2
+    float u2s, w2s, D2s; // direct form: kWd^2 * (-2u, -2w, |target|^2), so that sqrt() returns kWd * d
 };
 
 // fp32 leaf part L of the cost: J_leaf = Kbase + base_parent + L,
@@ -102,18 +103,20 @@ __device__ __forceinline__ float leaf_val(float a, float b, float r, float g, co
     return __fmaf_rn(10000.0f, t, acc);
 }
 
-// DIRECT form of the same leaf part (prefix pass 1, FAR regime), 9.5 FP32 ops + 1 MUFU per leaf instead of 14 + 1.5:
-//   L' = [kWd sqrt(D2 + num) + kc] + (q + eh)^2 + (g + nhh)^2,   kc = float(-kWd Dp), eh = e2/2, nhh = -h2/2
-// i.e. L' = L + (kWd Dp + kc) + eh^2 + nhh^2 in exact arithmetic; the node's base absorbs that constant in float64
-// (parent_setup's base_direct).  The distance term now carries the rounding of d itself (~2^-22 d kWd), so this
-// form only RANKS leaves for pass 1 with its own, wider error bound tol1 (prep_kernel); pass 2 filters with leaf_val.
+// DIRECT form of the same leaf part (prefix pass 1, FAR regime), 8 FP32 ops + 1 MUFU per leaf instead of 14 + 1.5:
+//   L' = sqrt(kWd^2 (D2 + num)) + (q + eh)^2 + (g + nhh)^2,   eh = e2/2, nhh = -h2/2
+// i.e. L' = L + kWd Dp + eh^2 + nhh^2 in exact arithmetic: the weight kWd sits under the root (the node's u2, w2, D2
+// are scaled by kWd^2 in float64 before rounding, the table's r by one FFMA), and the node constant is taken out of
+// the minimum altogether -- parent_setup's base_direct subtracts it in float64.  The value is therefore rounded at
+// the magnitude of kWd d (not of kWd reach), so this form only RANKS leaves for pass 1 with its own, wider error
+// bound tol1 (prep_kernel); pass 2 filters with leaf_val.
+constexpr float kWd2f = 1.0e8f;          // kWd^2, exact in fp32
 template <bool HEAD>
 __device__ __forceinline__ float leaf_val_direct(float a, float b, float r, float g, const ParentRegs &p) {
-    const float num = __fmaf_rn(p.u2, a, __fmaf_rn(p.w2, b, r));
-    const float s = sqrt_approx(p.D2 + num);
-    const float t = __fmaf_rn(10000.0f, s, p.kc);
+    const float dd = __fmaf_rn(p.u2s, a, __fmaf_rn(p.w2s, b, __fmaf_rn(kWd2f, r, p.D2s)));
+    const float s = sqrt_approx(dd);
     const float q = __fmaf_rn(p.nu, a, __fmaf_rn(p.nw, b, p.eh));
-    float acc = __fmaf_rn(q, q, t);
+    float acc = __fmaf_rn(q, q, s);
     if (HEAD) { const float gg = g + p.nhh; acc = __fmaf_rn(gg, gg, acc); }
     return acc;
 }
@@ -179,8 +182,10 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     // no child can do better than: one step straight at the target (d >= Dp - s_max, triangle inequality)
     // plus the most favourable line and heading offsets  (|q| <= wl s_max, |g| <= wh dphi_max)
     if (base_direct) {
-        pr.kc = (float)(-kWd * Dp); pr.eh = 0.5f * pr.e2; pr.nhh = -0.5f * pr.h2;
-        *base_direct = base0 + (-kWd * Dp - (double)pr.kc) - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
+        pr.eh = 0.5f * pr.e2; pr.nhh = -0.5f * pr.h2;
+        pr.u2s = (float)(-2.0 * kWd * kWd * u); pr.w2s = (float)(-2.0 * kWd * kWd * w);
+        pr.D2s = (float)(kWd * kWd * (Dp * Dp));
+        *base_direct = base0 - kWd * Dp - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
     }
     if (lower_bound)
         *lower_bound = base0 - kWd * a.g.smax + quad_min(2.0 * ep, P.wl * a.g.smax) + quad_min(-2.0 * hp, P.wh * a.g.dphimax);
@@ -328,11 +333,10 @@ __device__ __forceinline__ void decode_work(const LaunchArgs &a, unsigned long l
 template <bool HEAD>
 __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
                                                       float best) {
-    const float2 U2 = make_float2(pr.u2, pr.u2), W2 = make_float2(pr.w2, pr.w2);
-    const float2 D2 = make_float2(pr.D2, pr.D2), KC = make_float2(pr.kc, pr.kc);
+    const float2 U2 = make_float2(pr.u2s, pr.u2s), W2 = make_float2(pr.w2s, pr.w2s);
+    const float2 D2 = make_float2(pr.D2s, pr.D2s), K2 = make_float2(kWd2f, kWd2f);
     const float2 NU = make_float2(pr.nu, pr.nu), NW = make_float2(pr.nw, pr.nw);
     const float2 EH = make_float2(pr.eh, pr.eh), NHH = make_float2(pr.nhh, pr.nhh);
-    const float2 WD = make_float2(10000.0f, 10000.0f);
     constexpr int kUnroll = MPCB_UNROLL;
 #pragma unroll kUnroll
     for (int m = 0; m < npairs; ++m) {
@@ -340,10 +344,9 @@ __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__
         const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
         const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
         // leaf_val_direct on two leaves at a time
-        const float2 dd = __fadd2_rn(D2, __ffma2_rn(U2, A, __ffma2_rn(W2, B, R)));
-        const float2 t = __ffma2_rn(WD, make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)), KC);
+        const float2 dd = __ffma2_rn(U2, A, __ffma2_rn(W2, B, __ffma2_rn(K2, R, D2)));
         const float2 q = __ffma2_rn(NU, A, __ffma2_rn(NW, B, EH));
-        float2 acc = __ffma2_rn(q, q, t);
+        float2 acc = __ffma2_rn(q, q, make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)));
         if (HEAD) { const float2 gg = __fadd2_rn(G, NHH); acc = __ffma2_rn(gg, gg, acc); }
         best = fminf(best, fminf(acc.x, acc.y));
     }
@@ -354,15 +357,13 @@ __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__
 template <bool HEAD>
 __device__ __forceinline__ void prefix_min_loop_far2x2(const float4 *__restrict__ tab, int npairs, const ParentRegs &p0,
                                                        const ParentRegs &p1, float &best0, float &best1) {
-    const float2 U0 = make_float2(p0.u2, p0.u2), W0 = make_float2(p0.w2, p0.w2);
-    const float2 D0 = make_float2(p0.D2, p0.D2), K0 = make_float2(p0.kc, p0.kc);
+    const float2 U0 = make_float2(p0.u2s, p0.u2s), W0 = make_float2(p0.w2s, p0.w2s), D0 = make_float2(p0.D2s, p0.D2s);
     const float2 NU0 = make_float2(p0.nu, p0.nu), NW0 = make_float2(p0.nw, p0.nw);
     const float2 E0 = make_float2(p0.eh, p0.eh), H0 = make_float2(p0.nhh, p0.nhh);
-    const float2 U1 = make_float2(p1.u2, p1.u2), W1 = make_float2(p1.w2, p1.w2);
-    const float2 D1 = make_float2(p1.D2, p1.D2), K1 = make_float2(p1.kc, p1.kc);
+    const float2 U1 = make_float2(p1.u2s, p1.u2s), W1 = make_float2(p1.w2s, p1.w2s), D1 = make_float2(p1.D2s, p1.D2s);
     const float2 NU1 = make_float2(p1.nu, p1.nu), NW1 = make_float2(p1.nw, p1.nw);
     const float2 E1 = make_float2(p1.eh, p1.eh), H1 = make_float2(p1.nhh, p1.nhh);
-    const float2 WD = make_float2(10000.0f, 10000.0f);
+    const float2 K2 = make_float2(kWd2f, kWd2f);
     float b0 = best0, b1 = best1;
     constexpr int kUnroll = MPCB_UNROLL2;
 #pragma unroll kUnroll
@@ -370,13 +371,12 @@ __device__ __forceinline__ void prefix_min_loop_far2x2(const float4 *__restrict_
         const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
         const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
         const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
-        const float2 dd0 = __fadd2_rn(D0, __ffma2_rn(U0, A, __ffma2_rn(W0, B, R)));
-        const float2 dd1 = __fadd2_rn(D1, __ffma2_rn(U1, A, __ffma2_rn(W1, B, R)));
-        const float2 tt0 = __ffma2_rn(WD, make_float2(sqrt_approx(dd0.x), sqrt_approx(dd0.y)), K0);
-        const float2 tt1 = __ffma2_rn(WD, make_float2(sqrt_approx(dd1.x), sqrt_approx(dd1.y)), K1);
+        const float2 dd0 = __ffma2_rn(U0, A, __ffma2_rn(W0, B, __ffma2_rn(K2, R, D0)));
+        const float2 dd1 = __ffma2_rn(U1, A, __ffma2_rn(W1, B, __ffma2_rn(K2, R, D1)));
         const float2 q0 = __ffma2_rn(NU0, A, __ffma2_rn(NW0, B, E0));
         const float2 q1 = __ffma2_rn(NU1, A, __ffma2_rn(NW1, B, E1));
-        float2 acc0 = __ffma2_rn(q0, q0, tt0), acc1 = __ffma2_rn(q1, q1, tt1);
+        float2 acc0 = __ffma2_rn(q0, q0, make_float2(sqrt_approx(dd0.x), sqrt_approx(dd0.y)));
+        float2 acc1 = __ffma2_rn(q1, q1, make_float2(sqrt_approx(dd1.x), sqrt_approx(dd1.y)));
         if (HEAD) {
             const float2 g0 = __fadd2_rn(G, H0), g1 = __fadd2_rn(G, H1);
             acc0 = __ffma2_rn(g0, g0, acc0);
@@ -930,12 +930,14 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     P.tol1 = P.tol;
     if (prefix) {
         // direct form of the prefix pass 1 (leaf_val_direct), in units of 2^-23:
-        //   distance   kWd d (sqrt.approx 1 + roundings of D2, num, the sum ~0.75)        -> 3 kWd Dmax
-        //   kWd s + kc rounded at magnitude <= kWd smax, table/u2/w2 roundings             -> 2 kWd smax
-        //   (q + eh)^2 with |q + eh| <= E1: 1.5 ulp on the sum, squared, + the add         -> 4 E1^2
-        //   (g + nhh)^2 with |g + nhh| <= H1                                               -> 3 H1^2
+        //   distance   kWd d (sqrt.approx 1 + roundings of D2s, the FFMA chain under the root ~0.75) -> 3 kWd Dmax
+        //   roundings of the table entries and of u2s, w2s                                            -> 2 kWd smax
+        //   (q + eh)^2 with |q + eh| <= E1: 1.5 ulp on the sum, squared                                -> 4 E1^2
+        //   (g + nhh)^2 with |g + nhh| <= H1                                                           -> 3 H1^2
+        //   the two accumulating FFMAs round at the magnitude of the whole value (half an ulp each)    -> Vmax
         const double Dmax = P.d0 + Rtot, E1 = E + Q, H1 = Hh + Gl;
-        const double M1 = 3.0 * kWd * Dmax + 2.0 * kWd * smax + 4.0 * E1 * E1 + 3.0 * H1 * H1;
+        const double Vmax = kWd * Dmax + E1 * E1 + H1 * H1;
+        const double M1 = 3.0 * kWd * Dmax + 2.0 * kWd * smax + 4.0 * E1 * E1 + 3.0 * H1 * H1 + Vmax;
         P.tol1 = fmax(P.tol, 2.0 * M1 * 1.1920928955078125e-07 * tol_scale);
     }
     P.flags = f; P.pad = 0;

@@ -267,7 +267,8 @@ def _eps_model(s, origin, H, cost, prefix, smax, dphimax, direct=False):
         M += 1e4 * Rtot * 8 * max(1.0, H * dphimax / math.pi)
     if direct:
         d0 = math.hypot(xt - xs, yt - ys)
-        M1 = 3 * 1e4 * (d0 + Rtot) + 2 * 1e4 * smax + 4 * (E + Q) ** 2 + 3 * (Hh + Gl) ** 2
+        Vmax = 1e4 * (d0 + Rtot) + (E + Q) ** 2 + (Hh + Gl) ** 2      # the accumulating FFMAs round at this size
+        M1 = 3 * 1e4 * (d0 + Rtot) + 2 * 1e4 * smax + 4 * (E + Q) ** 2 + 3 * (Hh + Gl) ** 2 + Vmax
         M = max(M, M1)
     return M * 2.0 ** -23
 
