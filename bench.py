@@ -354,7 +354,7 @@ def run_gpu(args):
         fp32_peak = SM_COUNT * FP32_PER_CLK_SM * clk_hz
         per_gpu_rate = leaves_per_solve * n / (kern_ms * 1e-3)           # rollouts/s of one GPU, per step
         mufu_a = 2 * Hh + 1                                              # accounting A
-        issue_cyc = 10.5 if args.nodes_per_thread == 1 else 10.0         # issue cycles per rollout of the pair loop
+        issue_cyc = {1: 10.5, 4: 9.75}.get(args.nodes_per_thread, 10.0)         # issue cycles per rollout of the pair loop
         line = dict(
             metric="candidate rollouts/s (MPC inner loop)", value=value, unit="rollouts/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
@@ -376,7 +376,7 @@ def run_gpu(args):
                               issue_frac=per_gpu_rate * issue_cyc / fp32_peak),
                 hbm_gbs=(h2d + d2h) / (kern_ms * 1e-3) / 1e9, hbm_peak_gbs=pk["hbm_gbs"],
                 peak_src=f"{pk['src']} sm_max_mhz={pk['sm_max_mhz']:.0f} x {SM_COUNT} SMs x {MUFU_PER_CLK_SM} MUFU/clk/SM",
-                kernel=("leafwalk_kernel<1,true,1>" if stats["algo"] == nat.ALGO_LEAFWALK else "prefix_kernel<1,true>" if args.nodes_per_thread == 1 else "prefix2_kernel<true>") + " (pass 1)",
+                kernel=("leafwalk_kernel<1,true,1>" if stats["algo"] == nat.ALGO_LEAFWALK else "prefix_kernel<1,true>" if args.nodes_per_thread == 1 else f"prefixn_kernel<true,{args.nodes_per_thread or 2}>") + " (pass 1)",
                 kernel_ms_per_step=kern_ms),
             e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      solves_per_s=n * world * args.steps / float(te[0])),
@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--nodes-per-thread", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--nodes-per-thread", type=int, default=0, choices=[0, 1, 2, 4],
                     help="prefix pass 1: depth-(H-1) nodes per thread (0 = library default)")
     ap.add_argument("--algo", default="auto", choices=["auto", "prefix", "leafwalk"],
                     help="expansion kernel: prefix (default for this workload) or the one-thread-per-leaf design")

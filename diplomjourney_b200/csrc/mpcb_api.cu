@@ -336,7 +336,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
     else if (!strcmp(name, "nodes_per_thread")) {
-        if (value != 1.0 && value != 2.0) return fail(h, MPCB_ERR_INVALID, "nodes_per_thread must be 1 or 2");
+        if (value != 1.0 && value != 2.0 && value != 4.0) return fail(h, MPCB_ERR_INVALID, "nodes_per_thread must be 1, 2 or 4");
         h->npt = (int)value;
     }
     else return fail(h, MPCB_ERR_INVALID, "unknown option '%s'", name);

@@ -21,7 +21,10 @@
 #include "mpcb_types.cuh"
 
 #ifndef MPCB_UNROLL2
-#define MPCB_UNROLL2 4  // pairs per unrolled iteration of the two-node loop
+#define MPCB_UNROLL2 8  // pairs per unrolled iteration of the two-node loop (4: -3.5 %, profiles/r1j_variants.txt)
+#endif
+#ifndef MPCB_UNROLL4
+#define MPCB_UNROLL4 2  // pairs per unrolled iteration of the four-node loop (1, 2, 4 within 1.3 %)
 #endif
 #ifndef MPCB_UNROLL
 #define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (4..16 are within 1 %, profiles/r1b_variants.txt)
@@ -353,39 +356,38 @@ __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__
     return best;
 }
 
-// two depth-(H-1) nodes per thread on the same table entry: the two LDS.128 of a leaf pair feed both nodes
-template <bool HEAD>
-__device__ __forceinline__ void prefix_min_loop_far2x2(const float4 *__restrict__ tab, int npairs, const ParentRegs &p0,
-                                                       const ParentRegs &p1, float &best0, float &best1) {
-    const float2 U0 = make_float2(p0.u2s, p0.u2s), W0 = make_float2(p0.w2s, p0.w2s), D0 = make_float2(p0.D2s, p0.D2s);
-    const float2 NU0 = make_float2(p0.nu, p0.nu), NW0 = make_float2(p0.nw, p0.nw);
-    const float2 E0 = make_float2(p0.eh, p0.eh), H0 = make_float2(p0.nhh, p0.nhh);
-    const float2 U1 = make_float2(p1.u2s, p1.u2s), W1 = make_float2(p1.w2s, p1.w2s), D1 = make_float2(p1.D2s, p1.D2s);
-    const float2 NU1 = make_float2(p1.nu, p1.nu), NW1 = make_float2(p1.nw, p1.nw);
-    const float2 E1 = make_float2(p1.eh, p1.eh), H1 = make_float2(p1.nhh, p1.nhh);
+// NPT depth-(H-1) nodes per thread on the same table entry: the two LDS.128 of a leaf pair feed all of the thread's nodes
+template <bool HEAD, int NPT>
+__device__ __forceinline__ void prefix_min_loop_far2xN(const float4 *__restrict__ tab, int npairs,
+                                                       const ParentRegs (&p)[NPT], float (&best)[NPT]) {
+    float2 U[NPT], W[NPT], D[NPT], NU[NPT], NW[NPT], E[NPT], Hh[NPT];
+    float b[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        U[k] = make_float2(p[k].u2s, p[k].u2s); W[k] = make_float2(p[k].w2s, p[k].w2s);
+        D[k] = make_float2(p[k].D2s, p[k].D2s);
+        NU[k] = make_float2(p[k].nu, p[k].nu); NW[k] = make_float2(p[k].nw, p[k].nw);
+        E[k] = make_float2(p[k].eh, p[k].eh); Hh[k] = make_float2(p[k].nhh, p[k].nhh);
+        b[k] = best[k];
+    }
     const float2 K2 = make_float2(kWd2f, kWd2f);
-    float b0 = best0, b1 = best1;
-    constexpr int kUnroll = MPCB_UNROLL2;
+    constexpr int kUnroll = NPT == 2 ? MPCB_UNROLL2 : MPCB_UNROLL4;
 #pragma unroll kUnroll
     for (int m = 0; m < npairs; ++m) {
         const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
         const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
         const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
-        const float2 dd0 = __ffma2_rn(U0, A, __ffma2_rn(W0, B, __ffma2_rn(K2, R, D0)));
-        const float2 dd1 = __ffma2_rn(U1, A, __ffma2_rn(W1, B, __ffma2_rn(K2, R, D1)));
-        const float2 q0 = __ffma2_rn(NU0, A, __ffma2_rn(NW0, B, E0));
-        const float2 q1 = __ffma2_rn(NU1, A, __ffma2_rn(NW1, B, E1));
-        float2 acc0 = __ffma2_rn(q0, q0, make_float2(sqrt_approx(dd0.x), sqrt_approx(dd0.y)));
-        float2 acc1 = __ffma2_rn(q1, q1, make_float2(sqrt_approx(dd1.x), sqrt_approx(dd1.y)));
-        if (HEAD) {
-            const float2 g0 = __fadd2_rn(G, H0), g1 = __fadd2_rn(G, H1);
-            acc0 = __ffma2_rn(g0, g0, acc0);
-            acc1 = __ffma2_rn(g1, g1, acc1);
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const float2 dd = __ffma2_rn(U[k], A, __ffma2_rn(W[k], B, __ffma2_rn(K2, R, D[k])));
+            const float2 q = __ffma2_rn(NU[k], A, __ffma2_rn(NW[k], B, E[k]));
+            float2 acc = __ffma2_rn(q, q, make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)));
+            if (HEAD) { const float2 gg = __fadd2_rn(G, Hh[k]); acc = __ffma2_rn(gg, gg, acc); }
+            b[k] = fminf(b[k], fminf(acc.x, acc.y));
         }
-        b0 = fminf(b0, fminf(acc0.x, acc0.y));
-        b1 = fminf(b1, fminf(acc1.x, acc1.y));
     }
-    best0 = b0; best1 = b1;
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) best[k] = b[k];
 }
 
 // scalar flavour on the same pair table: NEAR regime, or a node sitting exactly on the line origin
@@ -522,13 +524,15 @@ prefix_kernel(const LaunchArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------ prefix, two nodes per thread
-// Pass 1, exhaustive only (option "nodes_per_thread" = 2): a 512-thread CTA covers the same four 256-node tiles as
-// prefix_kernel<1>, thread t holding node t and node t + 512 of the work item.  Same arithmetic per node, so the
-// segment minima (and everything downstream) are bit-identical to the one-node kernel.
-template <bool HEAD>
-__global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const LaunchArgs a) {
+// ------------------------------------------------------------------------------------ prefix, several nodes per thread
+// Pass 1, exhaustive only (option "nodes_per_thread" = 2 or 4): a CTA of 1024/NPT threads covers the same four 256-node
+// tiles as prefix_kernel<1>, thread t holding nodes t, t + 1024/NPT, ... of the work item (NPT = 4: two such CTAs per
+// SM).  Same arithmetic per node, so the segment minima (and everything downstream) are bit-identical to the
+// one-node kernel.
+template <bool HEAD, int NPT>
+__global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
+    constexpr int kCta = kPrefixCta / NPT;
     const int tid = threadIdx.x;
     const int S = a.g.S;
     const bool single = S <= kLeafChunk;
@@ -547,14 +551,15 @@ __global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const Launch
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;
         const bool origin_case = (P.flags & kFlagStartIsOrigin) != 0;
-        ParentRegs pr[2] = {};
-        bool near[2], special[2], active[2];
-        double base[2];
-        float best[2], Lspecial[2];
-        unsigned seg[2];
+        ParentRegs pr[NPT] = {};
+        bool near[NPT], special[NPT], active[NPT];
+        double base[NPT];
+        float best[NPT], Lspecial[NPT];
+        unsigned seg[NPT];
+        bool all = true;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const unsigned node = tid + k * (kPrefixCta / 2);
+        for (int k = 0; k < NPT; ++k) {
+            const unsigned node = tid + k * kCta;
             const unsigned long long tile = tile0 + node / kThreads;
             const unsigned long long p = a.u_begin + tile * kThreads + (node % kThreads);
             active[k] = tile < a.tiles_per_solve && p < a.u_end;
@@ -566,8 +571,8 @@ __global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const Launch
             special[k] = active[k] && origin_case && unmoved;
             if (!(near[k] || special[k])) base[k] = base_direct;
             Lspecial[k] = (float)(P.special - 0.25 * (double)pr[k].e2 * (double)pr[k].e2);
+            all = all && active[k] && !near[k] && !special[k];
         }
-        const bool both = active[0] && active[1] && !near[0] && !near[1] && !special[0] && !special[1];
         for (int c0 = 0; c0 < S; c0 += kLeafChunk) {
             const int cn = min(kLeafChunk, S - c0);
             if (!single) {
@@ -576,11 +581,11 @@ __global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const Launch
                 __syncthreads();
             }
             const int npairs = (cn + 1) >> 1;
-            if (both) {
-                prefix_min_loop_far2x2<HEAD>(s_leaf, npairs, pr[0], pr[1], best[0], best[1]);
+            if (all) {
+                prefix_min_loop_far2xN<HEAD, NPT>(s_leaf, npairs, pr, best);
             } else {
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < NPT; ++k) {
                     if (!active[k]) continue;
                     best[k] = (near[k] || special[k])
                                   ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr[k], near[k], special[k], Lspecial[k], best[k])
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(kPrefixCta / 2, 1) prefix2_kernel(const Launch
             }
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) publish_segmin(a, seg[k], active[k] ? base[k] + (double)best[k] : INFINITY);
+        for (int k = 0; k < NPT; ++k) publish_segmin(a, seg[k], active[k] ? base[k] + (double)best[k] : INFINITY);
     }
 }
 
@@ -1079,9 +1084,12 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
         if (pass == 1 && a.prune)   // small grids: nodes are cut lane by lane (the queue costs more than it saves there)
             return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
                         : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
+        if (pass == 1 && a.npt == 4)
+            return head ? launch_persistent(prefixn_kernel<true, 4>, a, pass, sm, sms, st, kPrefixCta / 4)
+                        : launch_persistent(prefixn_kernel<false, 4>, a, pass, sm, sms, st, kPrefixCta / 4);
         if (pass == 1 && a.npt == 2)
-            return head ? launch_persistent(prefix2_kernel<true>, a, pass, sm, sms, st, kPrefixCta / 2)
-                        : launch_persistent(prefix2_kernel<false>, a, pass, sm, sms, st, kPrefixCta / 2);
+            return head ? launch_persistent(prefixn_kernel<true, 2>, a, pass, sm, sms, st, kPrefixCta / 2)
+                        : launch_persistent(prefixn_kernel<false, 2>, a, pass, sm, sms, st, kPrefixCta / 2);
         if (pass == 1)
             return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixCta)
                         : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixCta);

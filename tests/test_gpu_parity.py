@@ -387,8 +387,8 @@ def test_skip_flag(solver, small_path):
 
 
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
-def test_two_nodes_per_thread_is_bit_identical(solver, cost):
-    """option nodes_per_thread=2 (exhaustive prefix pass 1 with two depth-(H-1) nodes per thread) does the same
+def test_several_nodes_per_thread_is_bit_identical(solver, cost):
+    """option nodes_per_thread=2 / 4 (exhaustive prefix pass 1 with several depth-(H-1) nodes per thread) does the same
     arithmetic per node: identical results to nodes_per_thread=1 and to the oracle, including ragged last tiles,
     a robot on the line origin, a robot next to its target (NEAR regime) and a chunked table (S > 1024)."""
     grids = [(np.linspace(0.0, 1.0, 11), np.linspace(-1.0, 1.0, 13), 3, 6),        # 143^2 nodes: ragged tiles
@@ -403,10 +403,11 @@ def test_two_nodes_per_thread_is_bit_identical(solver, cost):
             sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]
             solver.set_option("nodes_per_thread", 1)
             one = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
-            solver.set_option("nodes_per_thread", 2)
-            two = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
-            for k in ("index", "cost", "traj", "first_control"):
-                np.testing.assert_array_equal(two[k], one[k])
+            for npt in (2, 4):
+                solver.set_option("nodes_per_thread", npt)
+                two = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
+                for k in ("index", "cost", "traj", "first_control"):
+                    np.testing.assert_array_equal(two[k], one[k])
             for i, s in enumerate(sc):
                 _check(two, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, cost), H)
     finally:
