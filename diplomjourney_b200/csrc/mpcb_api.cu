@@ -20,6 +20,8 @@ cudaError_t launch_prep(cudaStream_t, long long, const double *, const double *,
 cudaError_t launch_pass(cudaStream_t, const LaunchArgs &, int pass, bool prefix, int sms);
 cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, unsigned *, unsigned *, int sms);
 cudaError_t launch_probe(cudaStream_t, const LaunchArgs &, int sms);
+cudaError_t launch_tilecut(cudaStream_t, const LaunchArgs &, unsigned long long g_begin, unsigned long long g_end,
+                           unsigned long long *list, unsigned *count);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
@@ -48,6 +50,7 @@ struct DevBuf {
 };
 
 constexpr unsigned long long kSegCap = 1ULL << 22;
+constexpr unsigned long long kTileBatch = 1ULL << 23;   // subtree cut: tiles per batch (survivor list <= 64 MiB)
 
 void fastdiv32_init(FastDiv32 &f, unsigned long long d64) {
     unsigned d = (unsigned)d64;
@@ -88,9 +91,10 @@ struct mpcb_handle_s {
     int small_path = 1;
     int dump_direct = 0;  // mpcb_dump_leaves_host, prefix: dump the values pass 1 ranks with
     int npt = 2;          // exhaustive prefix pass 1: nodes per thread (2: +6 %, tools/ubench)
+    bool subtree_cut = true;   // pruned pass 1, H >= 3: depth-(H-2) bound per 256-node tile before any node is set up
     int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
-    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub;
+    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list;
     DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
     DevBuf loop_log, loop_ticks, loop_status, small_in, small_out, fl_last, fl_k, fl_have, fl_flags, fl_count;
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
@@ -305,7 +309,7 @@ int mpcb_destroy(mpcb_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
-                      &h->lock, &h->ub, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
+                      &h->lock, &h->ub, &h->tile_list, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
                       &h->loop_status, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
                       &h->fl_count})
@@ -335,6 +339,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
+    else if (!strcmp(name, "subtree_cut")) h->subtree_cut = value != 0.0;
     else if (!strcmp(name, "nodes_per_thread")) {
         if (value != 1.0 && value != 2.0 && value != 4.0) return fail(h, MPCB_ERR_INVALID, "nodes_per_thread must be 1, 2 or 4");
         h->npt = (int)value;
@@ -403,7 +408,7 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     CK(h->bestIdx.ensure(sizeof(long long) * N));
     CK(h->lock.ensure(sizeof(int) * N));
     CK(h->ub.ensure(sizeof(unsigned long long) * N));
-    // misc: [0..7] work_count (u32) | [16..39] counters (3 x u64)
+    // misc: [0..3] work_count (u32) | [8..11] tile_count (u32, subtree cut) | [16..39] counters (3 x u64)
     unsigned *work_count = h->misc.as<unsigned>();
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
     CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
@@ -428,7 +433,23 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     if (a.prune) {
         CK(launch_probe(h->stream, a, h->sms)); ++launches;
     }
-    if (a.total_segs > 0) {
+    const unsigned __int128 tiles_all = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
+    if (a.total_segs > 0 && a.prune && h->subtree_cut && H >= 3 && tiles_all < ((unsigned __int128)1 << 63)) {
+        // subtree cut: batches of tiles go through the depth-(H-2) bound first; pass 1 walks the survivors only.
+        // No host synchronisation: the pass-1 grid is persistent over a device-side count.
+        const unsigned long long all = (unsigned long long)tiles_all;
+        const unsigned long long batch = std::min<unsigned long long>(all, kTileBatch);
+        CK(h->tile_list.ensure(sizeof(unsigned long long) * batch));
+        unsigned *tile_count = h->misc.as<unsigned>() + 2;
+        a.tile_list = h->tile_list.as<unsigned long long>();
+        a.tile_count = tile_count;
+        for (unsigned long long g0 = 0; g0 < all; g0 += batch) {
+            if (g0) CK(cudaMemsetAsync(tile_count, 0, sizeof(unsigned), h->stream));
+            CK(launch_tilecut(h->stream, a, g0, std::min(all, g0 + batch), h->tile_list.as<unsigned long long>(), tile_count)); ++launches;
+            CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
+        }
+        a.tile_list = nullptr; a.tile_count = nullptr;
+    } else if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
     }
     CK(launch_reduce_compact(h->stream, a, h->tau.as<double>(), h->worklist.as<unsigned>(), work_count, h->sms)); ++launches;

@@ -150,6 +150,30 @@ __device__ __forceinline__ double quad_min(double e, double Q) {
     return ae <= 2.0 * Q ? -0.25 * e * e : Q * (Q - ae);
 }
 
+// one step of the float64 prefix walk in the start frame: heading by the angle-addition recurrence
+__device__ __forceinline__ void walk_step(const double4 t, double &xi, double &eta, double &psi, double &cp, double &sp) {
+    double cn = cp * t.x - sp * t.y;
+    double sn = sp * t.x + cp * t.y;
+    cp = cn; sp = sn;
+    xi = fma(t.z, cp, xi);
+    eta = fma(t.z, sp, eta);
+    psi += t.w;
+}
+
+// Lower bound of J_rel over every leaf that lies `steps` further control steps below a node at (xi, eta, psi):
+// straight at the target all the way (d >= D - steps s_max, triangle inequality) plus the most favourable line
+// and heading offsets (|q| <= wl steps s_max, |g| <= wh steps dphi_max).
+__device__ __forceinline__ double subtree_lower_bound(const LaunchArgs &a, const SolveParams &P, double xi, double eta,
+                                                      double psi, int steps) {
+    const double relx = P.u0 - xi, rely = P.w0 - eta;
+    const double D = sqrt(relx * relx + rely * rely);
+    const double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
+    const double hp = P.hp0 - P.wh * psi;
+    const double base0 = kWd * (D - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
+    const double reach = steps * a.g.smax;
+    return base0 - kWd * reach + quad_min(2.0 * ep, P.wl * reach) + quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
+}
+
 __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
                                                unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved,
                                                double *lower_bound = nullptr, double *base_direct = nullptr) {
@@ -159,13 +183,7 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     for (int k = 0; k < D; ++k) {
         unsigned long long i = a.fd[k + 1].div(rem);
         rem -= i * a.fd[k + 1].d;
-        double4 t = ldg_d4(a.g.tab64 + i);
-        double cn = cp * t.x - sp * t.y;
-        double sn = sp * t.x + cp * t.y;
-        cp = cn; sp = sn;
-        xi = fma(t.z, cp, xi);
-        eta = fma(t.z, sp, eta);
-        psi += t.w;
+        walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
     }
     unmoved = (xi == 0.0 && eta == 0.0);
     double relx = P.u0 - xi, rely = P.w0 - eta;
@@ -432,11 +450,19 @@ prefix_kernel(const LaunchArgs a) {
     //  fully cut tile costs nothing more than its set-up)
     const unsigned groups = blockDim.x / kThreads;
     const unsigned long long qps = (a.tiles_per_solve + groups - 1) / groups;
+    const bool listed = PASS == 1 && PRUNE && a.tile_list != nullptr;     // walk the survivors of tilecut_kernel
     const unsigned long long nwork =
-        PASS == 1 ? (unsigned long long)a.N * qps : (unsigned long long)(*a.work_count) * a.tps;
+        listed ? (unsigned long long)(*a.tile_count)
+               : PASS == 1 ? (unsigned long long)a.N * qps : (unsigned long long)(*a.work_count) * a.tps;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
-        if (PASS == 1) {
+        if (listed) {
+            const unsigned long long g = a.tile_list[w];
+            n = (long long)(g / a.tiles_per_solve);
+            tile_lo = g - (unsigned long long)n * a.tiles_per_solve;
+            tile_hi = tile_lo + 1;
+            seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile_lo : tile_lo / a.tps));
+        } else if (PASS == 1) {
             n = (long long)(w / qps);
             const unsigned long long tile = (w - (unsigned long long)n * qps) * groups + (tid / kThreads);
             tile_lo = tile;
@@ -598,6 +624,49 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------ subtree cut (pruned pass 1)
+// Branch-and-bound one level up (H >= 3): one thread per 256-node tile.  The tile's depth-(H-1) nodes are children of
+// one depth-(H-2) node q (or of the few q the tile straddles); if the bound over ALL leaves two steps below every
+// such q exceeds the solve's running upper bound, no node of the tile can hold a leaf inside the refinement window
+// and the tile never reaches pass 1 (no set-up of its 256 nodes).  Survivors go to a list of global tile numbers that
+// the pruned pass-1 kernels then walk.  Exactness: same argument as the per-node cut.
+__global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, unsigned long long g_begin,
+                                                           unsigned long long g_end, unsigned long long *list,
+                                                           unsigned *count) {
+    const unsigned long long g = g_begin + blockIdx.x * (unsigned long long)kThreads + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    bool keep = false;
+    unsigned cut_nodes = 0;
+    if (g < g_end) {
+        const unsigned long long n = g / a.tiles_per_solve, tile = g - n * a.tiles_per_solve;
+        const SolveParams &P = a.sp[n];
+        if (!(P.flags & kFlagSkip)) {
+            const unsigned long long S = (unsigned long long)a.g.S;
+            const unsigned long long p_lo = a.u_begin + tile * kThreads;
+            const unsigned long long p_hi = min(p_lo + (unsigned long long)kThreads, a.u_end);     // exclusive
+            const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
+            for (unsigned long long q = p_lo / S; q <= (p_hi - 1) / S && !keep; ++q) {
+                double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
+                unsigned long long rem = q;
+                for (int k = 0; k < a.H - 2; ++k) {           // fd[k + 2].d = S^(H-3-k): digits of a depth-(H-2) node
+                    unsigned long long i = a.fd[k + 2].div(rem);
+                    rem -= i * a.fd[k + 2].d;
+                    walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
+                }
+                keep = !(subtree_lower_bound(a, P, xi, eta, psi, 2) > bound);      // NaN bounds never cut
+            }
+            if (!keep) cut_nodes = (unsigned)(p_hi - p_lo);
+        }
+    }
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    unsigned base = 0;
+    if (lane == 0 && mk) base = atomicAdd(count, (unsigned)__popc(mk));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) list[base + __popc(mk & ((1u << lane) - 1u))] = g;
+    for (int o = 16; o > 0; o >>= 1) cut_nodes += __shfl_xor_sync(0xffffffffu, cut_nodes, o);
+    if (lane == 0 && cut_nodes) atomicAdd(a.counters + 2, (unsigned long long)cut_nodes);
+}
+
 // ------------------------------------------------------------------------------------ prefix, pruned (pass 1)
 // Exact branch-and-bound (option prune).  Cutting nodes lane by lane leaves warps with one or two live lanes --
 // the promising nodes are scattered (a few steering directions per speed) -- so every WARP runs on its own:
@@ -651,12 +720,22 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
     };
 
     const unsigned long long wtps = (a.u_end - a.u_begin + 31) / 32;      // 32-node warp tiles per solve
-    const unsigned long long nww = (unsigned long long)a.N * wtps;
+    const bool listed = a.tile_list != nullptr;                           // walk the survivors of tilecut_kernel
+    const unsigned long long nww = listed ? (unsigned long long)(*a.tile_count) * (kThreads / 32)
+                                          : (unsigned long long)a.N * wtps;
     const unsigned long long gw = (unsigned long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const unsigned long long GW = (unsigned long long)gridDim.x * (kThreads / 32);
     for (unsigned long long ww = gw; ww < nww; ww += GW) {
-        const long long n = (long long)(ww / wtps);
-        const unsigned long long wt = ww - (unsigned long long)n * wtps;
+        long long n; unsigned long long wt;
+        if (listed) {
+            const unsigned long long g = a.tile_list[ww / (kThreads / 32)];
+            n = (long long)(g / a.tiles_per_solve);
+            wt = (g - (unsigned long long)n * a.tiles_per_solve) * (kThreads / 32) + ww % (kThreads / 32);
+            if (wt >= wtps) continue;                                     // ragged last tile
+        } else {
+            n = (long long)(ww / wtps);
+            wt = ww - (unsigned long long)n * wtps;
+        }
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;
         const unsigned long long tile = wt / (kThreads / 32);
@@ -1104,6 +1183,13 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
     return head ? MPCB_LW_KIND(2, true) : MPCB_LW_KIND(2, false);
 #undef MPCB_LW_KIND
 #undef MPCB_LW
+}
+
+cudaError_t launch_tilecut(cudaStream_t st, const LaunchArgs &a, unsigned long long g_begin, unsigned long long g_end,
+                           unsigned long long *list, unsigned *count) {
+    const unsigned long long blocks = (g_end - g_begin + kThreads - 1) / kThreads;
+    tilecut_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(a, g_begin, g_end, list, count);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_probe(cudaStream_t st, const LaunchArgs &a, int sms) {

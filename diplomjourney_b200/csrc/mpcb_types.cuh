@@ -115,6 +115,10 @@ struct LaunchArgs {
     unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
+    // subtree cut (pruned pass 1, H >= 3): tiles that survived the depth-(H-2) bound, as global tile numbers
+    // n * tiles_per_solve + tile; null = walk every tile
+    const unsigned long long *tile_list;
+    const unsigned *tile_count;
     int dump_direct;                       // prefix dump: direct (pass-1) form instead of the pass-2 form
     int npt;                               // depth-(H-1) nodes per thread in the exhaustive prefix pass 1 (1 or 2)
     int i0_begin, i0_end;                   // first-control range of this launch (probe)

@@ -307,32 +307,43 @@ def test_fp32_stage_error_stays_inside_the_refinement_window(solver, algo, cost)
 
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
 def test_branch_and_bound_is_exact(solver, cost):
-    """option prune=1 (default) skips depth-(H-1) nodes that provably cannot hold the argmin: the answers must be
-    bit-identical to prune=0 (every leaf evaluated) and to the oracle, on wide-speed grids where most nodes are cut
-    and on the narrow acceleration window where few are."""
-    grids = [(np.linspace(0.0, 1.0, 16), np.linspace(-np.radians(60), np.radians(60), 16), 3, 8),
-             (C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0), 3, 4),
-             (np.linspace(0.0, 1.0, 6), np.linspace(-1.0, 1.0, 7), 4, 8)]
+    """option prune=1 (default) skips depth-(H-1) nodes that provably cannot hold the argmin and, with subtree_cut=1
+    (default, H >= 3), whole 256-node tiles below depth-(H-2) nodes that cannot: the answers must be bit-identical to
+    prune=0 (every leaf evaluated) and to the oracle -- on wide-speed grids where most nodes are cut, on the narrow
+    acceleration window where few are, on a deep tree with a tiny grid (a tile straddles many depth-(H-2) nodes) and
+    on a grid with S > 1024 restricted to a few first controls (warp-queue kernel walking the survivor list)."""
+    grids = [(np.linspace(0.0, 1.0, 16), np.linspace(-np.radians(60), np.radians(60), 16), 3, 8, None),
+             (C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0), 3, 4, None),
+             (np.linspace(0.0, 1.0, 6), np.linspace(-1.0, 1.0, 7), 4, 8, None),
+             (np.linspace(0.0, 1.0, 3), np.linspace(-1.0, 1.0, 4), 5, 6, None),
+             (np.linspace(0.0, 1.0, 30), np.linspace(-1.0, 1.0, 50), 3, 2, (1480, 1500))]
     solver.set_option("algo", nat.ALGO_PREFIX)
     try:
-        for V, B, H, n in grids:
+        for V, B, H, n, i0 in grids:
             solver.set_grid(V, B, L, DT, VMIN)
             sc = C.random_scenarios(n, 500 + H)
             sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]                      # one robot already next to its target
+            args = (nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
             solver.set_option("prune", 0)
-            full = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
+            full = solver.solve(*args, i0_range=i0)
             assert solver.stats()["pruned_units"] == 0
             solver.set_option("prune", 1)
-            cut = solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2])
-            st = solver.stats()
-            np.testing.assert_array_equal(cut["index"], full["index"])
-            np.testing.assert_array_equal(cut["cost"], full["cost"])
-            np.testing.assert_array_equal(cut["traj"], full["traj"])
-            for i, s in enumerate(sc):
-                _check(cut, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, cost), H)
-            if len(V) == 16:
-                assert st["pruned_units"] > 0.2 * st["units"] * n          # v in [0,1]: many nodes cannot win
+            pruned = {}
+            for subtree in (0, 1):
+                solver.set_option("subtree_cut", subtree)
+                cut = solver.solve(*args, i0_range=i0)
+                st = solver.stats()
+                pruned[subtree] = st["pruned_units"]
+                assert 0 <= st["pruned_units"] <= st["units"] * n
+                np.testing.assert_array_equal(cut["index"], full["index"])
+                np.testing.assert_array_equal(cut["cost"], full["cost"])
+                np.testing.assert_array_equal(cut["traj"], full["traj"])
+                for i, s in enumerate(sc):
+                    _check(cut, i, K.solve_full(s[:3], s[3:], s[:2], V, B, H, cost, i0_range=i0), H)
+                if len(V) == 16:
+                    assert st["pruned_units"] > 0.2 * st["units"] * n      # v in [0,1]: many nodes cannot win
     finally:
+        solver.set_option("subtree_cut", 1)
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
 
