@@ -114,8 +114,8 @@ def cpu_sample(wl, seconds_target=12.0, procs=None):
     S = len(wl["V"]) * len(wl["B"])
     if wl["H"] != 3:
         raise SystemExit("the reference CPU path is hard-coded to H=3 (math_model.py:160-186)")
-    # ~90 us per leaf per core -> pick the number of second-level subtrees per process
-    n_i1 = max(1, min(S, int(seconds_target / (90e-6 * S))))
+    # ~33 us per leaf per core (measured on the B200 box's hosts) -> second-level subtrees per process for ~12 s
+    n_i1 = max(1, min(S, int(seconds_target / (33e-6 * S))))
     leaves, wall, per = P.timed_sample_full(list(wl["V"]), list(wl["B"]), scen, "mm", n_i1, procs)
     return dict(value=leaves / wall, unit="rollouts/s", cores=procs, kind="port",
                 sample=f"{procs} processes x {n_i1} second-level subtrees ({n_i1 * S} leaves each) of the FULL H=3 "
