@@ -22,6 +22,9 @@ cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, un
 cudaError_t launch_probe(cudaStream_t, const LaunchArgs &, int sms);
 cudaError_t launch_tilecut(cudaStream_t, const LaunchArgs &, unsigned long long g_begin, unsigned long long g_end,
                            unsigned long long *list, unsigned *count);
+cudaError_t launch_frontier_expand(cudaStream_t, const LaunchArgs &, int k, const unsigned long long *src,
+                                   const unsigned *src_count, unsigned long long *dst, unsigned *dst_count,
+                                   unsigned *overflow, int sms);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
@@ -51,6 +54,7 @@ struct DevBuf {
 
 constexpr unsigned long long kSegCap = 1ULL << 22;
 constexpr unsigned long long kTileBatch = 1ULL << 23;   // subtree cut: tiles per batch (survivor list <= 64 MiB)
+constexpr unsigned long long kFrontierCap = 1ULL << 22; // frontier descent: entries per list (two lists = the tile list's 64 MiB)
 
 void fastdiv32_init(FastDiv32 &f, unsigned long long d64) {
     unsigned d = (unsigned)d64;
@@ -91,7 +95,8 @@ struct mpcb_handle_s {
     int small_path = 1;
     int dump_direct = 0;  // mpcb_dump_leaves_host, prefix: dump the values pass 1 ranks with
     int npt = 2;          // exhaustive prefix pass 1: nodes per thread (2: +6 %, tools/ubench)
-    bool subtree_cut = true;   // pruned pass 1, H >= 3: depth-(H-2) bound per 256-node tile before any node is set up
+    unsigned long long frontier_cap = kFrontierCap;   // entries per frontier list (option, diagnostics: a tiny value forces the fallback)
+    int subtree_cut = 2;       // pruned pass 1, H >= 3: 0 off, 1 depth-(H-2) bound per 256-node tile, 2 auto (frontier descent from the root for trees of more than one tile batch), 3 frontier always
     int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
     DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list;
@@ -339,7 +344,14 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
-    else if (!strcmp(name, "subtree_cut")) h->subtree_cut = value != 0.0;
+    else if (!strcmp(name, "subtree_cut")) {
+        if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0) return fail(h, MPCB_ERR_INVALID, "subtree_cut must be 0, 1, 2 or 3");
+        h->subtree_cut = (int)value;
+    }
+    else if (!strcmp(name, "frontier_cap")) {
+        if (!(value >= 1.0 && value <= (double)(1ULL << 28))) return fail(h, MPCB_ERR_INVALID, "frontier_cap out of range [1, 2^28]");
+        h->frontier_cap = (unsigned long long)value;
+    }
     else if (!strcmp(name, "nodes_per_thread")) {
         if (value != 1.0 && value != 2.0 && value != 4.0) return fail(h, MPCB_ERR_INVALID, "nodes_per_thread must be 1, 2 or 4");
         h->npt = (int)value;
@@ -408,7 +420,8 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     CK(h->bestIdx.ensure(sizeof(long long) * N));
     CK(h->lock.ensure(sizeof(int) * N));
     CK(h->ub.ensure(sizeof(unsigned long long) * N));
-    // misc: [0..3] work_count (u32) | [8..11] tile_count (u32, subtree cut) | [16..39] counters (3 x u64)
+    // misc: [0..3] work_count (u32) | [8..11] tile_count (u32, subtree cut) | [16..47] counters (4 x u64) |
+    //       [48..55] frontier counts (2 x u32) | [56..59] frontier overflow flag (u32)
     unsigned *work_count = h->misc.as<unsigned>();
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
     CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
@@ -435,20 +448,53 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     }
     const unsigned __int128 tiles_all = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
     if (a.total_segs > 0 && a.prune && h->subtree_cut && H >= 3 && tiles_all < ((unsigned __int128)1 << 63)) {
-        // subtree cut: batches of tiles go through the depth-(H-2) bound first; pass 1 walks the survivors only.
-        // No host synchronisation: the pass-1 grid is persistent over a device-side count.
+        // Subtree cut.  Tile path: batches of tiles go through the depth-(H-2) bound, pass 1 walks the surviving
+        // tiles -- all enqueued, no host synchronisation (every grid is persistent over a device-side count).
+        // Frontier descent (trees of more than one tile batch, where testing every tile is itself the cost):
+        // survivors of depth k expand to depth k+1 down to depth H-2 and pass 1 walks their children; the host then
+        // reads ONE flag -- did a frontier outgrow its list? -- and only in that case runs the tile path instead.
         const unsigned long long all = (unsigned long long)tiles_all;
         const unsigned long long batch = std::min<unsigned long long>(all, kTileBatch);
-        CK(h->tile_list.ensure(sizeof(unsigned long long) * batch));
+        unsigned long long deepest = 0;                       // N * S^(H-2): the last frontier if nothing is cut
+        const bool ids_fit = pow_checked((unsigned long long)h->g.S, H - 2, deepest) &&
+                             (unsigned __int128)deepest * (unsigned long long)N < ((unsigned __int128)1 << 62);
+        const bool frontier = ids_fit && (h->subtree_cut == 3 || (h->subtree_cut == 2 && all > kTileBatch));
+        const unsigned long long cap = std::min<unsigned long long>(h->frontier_cap, std::max<unsigned long long>(deepest * (unsigned long long)N, 1));
+        CK(h->tile_list.ensure(sizeof(unsigned long long) * std::max(batch, frontier ? 2 * cap : 0ULL)));
+        unsigned long long *lists = h->tile_list.as<unsigned long long>();
         unsigned *tile_count = h->misc.as<unsigned>() + 2;
-        a.tile_list = h->tile_list.as<unsigned long long>();
-        a.tile_count = tile_count;
-        for (unsigned long long g0 = 0; g0 < all; g0 += batch) {
-            if (g0) CK(cudaMemsetAsync(tile_count, 0, sizeof(unsigned), h->stream));
-            CK(launch_tilecut(h->stream, a, g0, std::min(all, g0 + batch), h->tile_list.as<unsigned long long>(), tile_count)); ++launches;
+        unsigned *q_counts = h->misc.as<unsigned>() + 12;     // two ping-pong counts
+        unsigned *q_overflow = h->misc.as<unsigned>() + 14;
+        a.q_overflow = q_overflow;
+        bool tiles_needed = true;
+        if (frontier) {
+            a.q_cap = (unsigned)cap;
+            a.gate = 1;                                       // pass 1 must not walk a truncated list
+            for (int k = 0; k <= H - 3; ++k) {
+                unsigned *dst_count = q_counts + (k & 1);
+                if (k >= 2) CK(cudaMemsetAsync(dst_count, 0, sizeof(unsigned), h->stream));
+                CK(launch_frontier_expand(h->stream, a, k, k ? lists + ((k - 1) & 1) * cap : nullptr, k ? q_counts + ((k - 1) & 1) : nullptr,
+                                          lists + (k & 1) * cap, dst_count, q_overflow, h->sms)); ++launches;
+            }
+            a.q_list = lists + ((H - 3) & 1) * cap;
+            a.q_count = q_counts + ((H - 3) & 1);
             CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
+            a.q_list = nullptr; a.q_count = nullptr; a.gate = 0;
+            unsigned overflowed = 0;
+            CK(cudaMemcpyAsync(&overflowed, q_overflow, sizeof overflowed, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            tiles_needed = overflowed != 0;
         }
-        a.tile_list = nullptr; a.tile_count = nullptr;
+        if (tiles_needed) {
+            a.tile_list = lists;
+            a.tile_count = tile_count;
+            for (unsigned long long g0 = 0; g0 < all; g0 += batch) {
+                if (g0 || frontier) CK(cudaMemsetAsync(tile_count, 0, sizeof(unsigned), h->stream));
+                CK(launch_tilecut(h->stream, a, g0, std::min(all, g0 + batch), lists, tile_count)); ++launches;
+                CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
+            }
+            a.tile_list = nullptr; a.tile_count = nullptr;
+        }
     } else if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
     }

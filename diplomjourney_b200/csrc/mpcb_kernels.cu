@@ -82,6 +82,7 @@ struct ParentRegs {
     float e2, h2;      // 2 * wl*signed line distance of the parent, 2 * wh*(theta - phi_parent)
     float eh, nhh;     // direct form (prefix pass 1): e2/2, -h2/2
     float u2s, w2s, D2s; // direct form: kWd^2 * (-2u, -2w, |target|^2), so that sqrt() returns kWd * d
+                         // (leafwalk, whose leaves are not one table step away: u2s, w2s = kWd * (u, w) instead)
 };
 
 // fp32 leaf part L of the cost: J_leaf = Kbase + base_parent + L,
@@ -139,7 +140,29 @@ __device__ __forceinline__ double start_as_parent(const SolveParams &P, ParentRe
     const double base = (P.flags & kFlagNear) ? rem : 0.0;
     pr.nu = (float)P.nx0; pr.nw = (float)P.ny0;
     pr.e2 = (float)(2.0 * P.e0); pr.h2 = (float)(2.0 * P.hp0);
+    // direct form (pass 1): leaf_walk_direct
+    pr.u2s = (float)(kWd * P.u0); pr.w2s = (float)(kWd * P.w0);
+    pr.eh = (float)P.e0; pr.nhh = (float)(-P.hp0);
     return base;
+}
+
+// what the direct form of the leafwalk measures from: L' = L + kWd d0 + eh^2 + nhh^2 (see leaf_walk_direct)
+__device__ __forceinline__ double start_direct_offset(const SolveParams &P, const ParentRegs &pr) {
+    return kWd * P.d0 + (double)pr.eh * (double)pr.eh + (double)pr.nhh * (double)pr.nhh;
+}
+
+// DIRECT form for a leaf reached by a walk (leafwalk pass 1): (xi, eta, psi) is the leaf in the start frame,
+//   L' = kWd |(u, w) - (xi, eta)| + (q + e0)^2 + (wh psi - hp0)^2,
+// 9 FP32 ops + 1 MUFU against 15 + 2 for leaf_val, and no FAR/NEAR distinction.  Like leaf_val_direct it is rounded at
+// the magnitude of kWd d and only RANKS (tol1); pass 2 filters with leaf_val.
+template <bool HEAD>
+__device__ __forceinline__ float leaf_walk_direct(float xi, float eta, float psi, const ParentRegs &p) {
+    const float dx = __fmaf_rn(-10000.0f, xi, p.u2s), dy = __fmaf_rn(-10000.0f, eta, p.w2s);
+    const float s = sqrt_approx(__fmaf_rn(dx, dx, dy * dy));
+    const float q = __fmaf_rn(p.nu, xi, __fmaf_rn(p.nw, eta, p.eh));
+    float acc = __fmaf_rn(q, q, s);
+    if (HEAD) { const float gg = __fmaf_rn(3.16227766016837952f, psi, p.nhh); acc = __fmaf_rn(gg, gg, acc); }
+    return acc;
 }
 
 // float64 walk of the prefix (i_0 .. i_{H-2}) of depth-(H-1) node p in the start frame, then the
@@ -325,6 +348,23 @@ __device__ __forceinline__ void publish_segmin(const LaunchArgs &a, unsigned seg
         atomicMin(reinterpret_cast<unsigned long long *>(a.segmin) + seg, ordered_key(v));
 }
 
+// the same when the lanes of a warp may belong to different segments (frontier mode: a warp's 32 nodes can straddle
+// a 256-node tile boundary when S is not a multiple of 32)
+__device__ __forceinline__ void publish_segmin_lanes(const LaunchArgs &a, unsigned seg, double v) {
+    const unsigned live = __ballot_sync(0xffffffffu, v < INFINITY);
+    if (!live) return;
+    const unsigned seg0 = __shfl_sync(0xffffffffu, seg, __ffs(live) - 1);
+    if (__all_sync(0xffffffffu, !(v < INFINITY) || seg == seg0)) publish_segmin(a, seg0, v);
+    else if (v < INFINITY) atomicMin(reinterpret_cast<unsigned long long *>(a.segmin) + seg, ordered_key(v));
+}
+
+// gated launches: the frontier path and its tile-path fallback are both enqueued; one of them returns at once
+__device__ __forceinline__ bool gate_closed(const LaunchArgs &a) {
+    if (a.gate == 0) return false;
+    const bool overflow = *(volatile const unsigned *)a.q_overflow != 0;
+    return a.gate == 1 ? overflow : !overflow;
+}
+
 // work item -> (segment, solve, tile range).  PASS 1 walks all segments, PASS 2 the work list.
 template <int PASS>
 __device__ __forceinline__ void decode_work(const LaunchArgs &a, unsigned long long w, unsigned &seg,
@@ -427,7 +467,7 @@ __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict
 // children is compared with the solve's running upper bound; nodes that provably cannot reach the refinement
 // window are skipped lane by lane (a queue that compacts the survivors across tiles was measured 1.3-4x SLOWER:
 // it serialises the float64 set-up and the fp32 pair loop that otherwise overlap between warps).
-template <int PASS, bool HEAD, bool PRUNE = false>
+template <int PASS, bool HEAD, bool PRUNE = false, bool QMODE = false>
 __global__ void __launch_bounds__((PASS == 1 && !PRUNE) ? kPrefixCta : kThreads, (PASS == 1 && PRUNE) ? 4 : 1)
 prefix_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
@@ -450,13 +490,30 @@ prefix_kernel(const LaunchArgs a) {
     //  fully cut tile costs nothing more than its set-up)
     const unsigned groups = blockDim.x / kThreads;
     const unsigned long long qps = (a.tiles_per_solve + groups - 1) / groups;
-    const bool listed = PASS == 1 && PRUNE && a.tile_list != nullptr;     // walk the survivors of tilecut_kernel
+    // QMODE (a separate instantiation, so that the tile walk keeps its registers): walk the children of the frontier's survivors
+    constexpr bool qmode = PASS == 1 && PRUNE && QMODE;
+    const bool listed = PASS == 1 && PRUNE && !QMODE && a.tile_list != nullptr;     // walk the survivors of tilecut_kernel
+    if (PASS == 1 && PRUNE && gate_closed(a)) return;
+    const unsigned qrounds = (unsigned)((S + kThreads - 1) / kThreads);   // 256-node rounds per depth-(H-2) node
+    if (qmode && blockIdx.x == 0 && tid == 0) atomicAdd(a.counters + 2, a.counters[3]);   // subtrees the descent cut
     const unsigned long long nwork =
-        listed ? (unsigned long long)(*a.tile_count)
-               : PASS == 1 ? (unsigned long long)a.N * qps : (unsigned long long)(*a.work_count) * a.tps;
+        qmode ? (unsigned long long)min(*a.q_count, a.q_cap) * qrounds
+        : listed ? (unsigned long long)(*a.tile_count)
+                 : PASS == 1 ? (unsigned long long)a.N * qps : (unsigned long long)(*a.work_count) * a.tps;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
-        if (listed) {
+        unsigned long long p_q = 0; bool in_q = false;                    // frontier mode: this thread's node
+        if (qmode) {
+            const unsigned long long e = w / qrounds;
+            const unsigned c = (unsigned)(w - e * qrounds) * kThreads + tid;
+            const unsigned long long g = a.q_list[e];
+            n = (long long)a.fd[1].div(g);                                // fd[1].d = S^(H-2)
+            p_q = (g - (unsigned long long)n * a.fd[1].d) * (unsigned long long)S + c;
+            in_q = c < (unsigned)S;
+            tile_lo = in_q ? (p_q - a.u_begin) / kThreads : 0;            // per lane
+            tile_hi = tile_lo + 1;
+            seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile_lo : tile_lo / a.tps));
+        } else if (listed) {
             const unsigned long long g = a.tile_list[w];
             n = (long long)(g / a.tiles_per_solve);
             tile_lo = g - (unsigned long long)n * a.tiles_per_solve;
@@ -480,8 +537,8 @@ prefix_kernel(const LaunchArgs a) {
         double bJ = INFINITY; long long bj = -1;
         {
             const unsigned long long tile = tile_lo;
-            const unsigned long long p = a.u_begin + tile * kThreads + (tid % kThreads);
-            const bool in_range = tile < tile_hi && p < a.u_end;
+            const unsigned long long p = qmode ? p_q : a.u_begin + tile * kThreads + (tid % kThreads);
+            const bool in_range = qmode ? in_q : (tile < tile_hi && p < a.u_end);
             ParentRegs pr = {};
             bool near = false, unmoved = false;
             double base = 0.0, base_direct = 0.0, lb = -INFINITY;
@@ -545,7 +602,8 @@ prefix_kernel(const LaunchArgs a) {
                 if ((tid & 31) == 0 && v < INFINITY) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol1));
             }
         }
-        if (PASS == 1) publish_segmin(a, seg, segbest);
+        if (PASS == 1 && qmode) publish_segmin_lanes(a, seg, segbest);
+        else if (PASS == 1) publish_segmin(a, seg, segbest);
         else publish_best(a, n, bJ, bj, s_J, s_j);
     }
 }
@@ -624,6 +682,70 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
     }
 }
 
+// ------------------------------------------------------------------------------------ frontier descent (pruned pass 1)
+// Branch-and-bound from the top (H >= 3): the frontier of depth-k nodes that may still hold the argmin is expanded
+// to depth k+1 -- one thread per (survivor, child): float64 walk of the child's k+1 controls, bound over all leaves
+// H-k-1 steps below it against the solve's running upper bound -- until depth H-2; pass 1 then sets up and scores
+// only the children of those survivors.  Cut subtrees are never enumerated at all, which is what makes 1e15-leaf
+// trees a matter of milliseconds when the bound bites.  Node ids are global: n * S^k + index, so a child is simply
+// id * S + c.  The lists have a fixed capacity; a frontier that outgrows it raises *overflow and the (already
+// enqueued, gated) tile path does the solve instead -- no host round trip either way.
+__global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchArgs a, int k,
+                                                                   const unsigned long long *__restrict__ src,
+                                                                   const unsigned *src_count,
+                                                                   unsigned long long *__restrict__ dst,
+                                                                   unsigned *dst_count, unsigned *overflow) {
+    if (*(volatile unsigned *)overflow) return;
+    const unsigned long long S = (unsigned long long)a.g.S;
+    const unsigned long long nsrc = src ? (unsigned long long)min(*src_count, a.q_cap) : (unsigned long long)a.N;
+    const unsigned long long c_lo = src ? 0ULL : (unsigned long long)a.i0_begin;
+    const unsigned long long nchild = src ? S : (unsigned long long)(a.i0_end - a.i0_begin);
+    const unsigned long long total = nsrc * nchild;
+    const FastDiv64 fdn = a.fd[a.H - 2 - k];           // divisor S^(k+1): child id -> (solve, node index at depth k+1)
+    const int steps = a.H - (k + 1);                   // control steps below a depth-(k+1) node
+    const unsigned long long below = a.fd[k + 1].d;    // S^(H-2-k) depth-(H-1) nodes below it
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long cut = 0;
+    for (unsigned long long t0 = blockIdx.x * (unsigned long long)kThreads + (threadIdx.x & ~31u); t0 < total;
+         t0 += (unsigned long long)gridDim.x * kThreads) {
+        const unsigned long long t = t0 + lane;
+        bool keep = false;
+        unsigned long long child = 0;
+        if (t < total) {
+            const unsigned long long e = t / nchild;
+            child = (src ? src[e] : e) * S + (t - e * nchild + c_lo);
+            const unsigned long long n = fdn.div(child);
+            const SolveParams &P = a.sp[n];
+            if (!(P.flags & kFlagSkip)) {
+                unsigned long long rem = child - n * fdn.d;
+                double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
+                for (int m = 0; m <= k; ++m) {         // digit m has weight S^(k-m) = fd[H-1-k+m].d
+                    const FastDiv64 &fd = a.fd[a.H - 1 - k + m];
+                    const unsigned long long i = fd.div(rem);
+                    rem -= i * fd.d;
+                    walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
+                }
+                const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
+                keep = !(subtree_lower_bound(a, P, xi, eta, psi, steps) > bound);      // NaN bounds never cut
+                if (!keep) cut += below;
+            }
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        if (mk) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(dst_count, (unsigned)__popc(mk));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned slot = base + __popc(mk & ((1u << lane) - 1u));
+            if (keep) {
+                if (slot < a.q_cap) dst[slot] = child;
+                else *overflow = 1u;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) cut += __shfl_xor_sync(0xffffffffu, cut, o);
+    if (lane == 0 && cut) atomicAdd(a.counters + 3, cut);
+}
+
 // ------------------------------------------------------------------------------------ subtree cut (pruned pass 1)
 // Branch-and-bound one level up (H >= 3): one thread per 256-node tile.  The tile's depth-(H-1) nodes are children of
 // one depth-(H-2) node q (or of the few q the tile straddles); if the bound over ALL leaves two steps below every
@@ -633,6 +755,7 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
 __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, unsigned long long g_begin,
                                                            unsigned long long g_end, unsigned long long *list,
                                                            unsigned *count) {
+    if (gate_closed(a)) return;
     const unsigned long long g = g_begin + blockIdx.x * (unsigned long long)kThreads + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     bool keep = false;
@@ -686,7 +809,7 @@ struct __align__(8) QEntry {
 };
 constexpr int kWarpQueue = 64;
 
-template <bool HEAD>
+template <bool HEAD, bool QMODE = false>
 __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const LaunchArgs a) {
     extern __shared__ unsigned char s_raw[];
     QEntry *q = reinterpret_cast<QEntry *>(s_raw) + (threadIdx.x >> 5) * kWarpQueue;
@@ -720,14 +843,26 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
     };
 
     const unsigned long long wtps = (a.u_end - a.u_begin + 31) / 32;      // 32-node warp tiles per solve
-    const bool listed = a.tile_list != nullptr;                           // walk the survivors of tilecut_kernel
-    const unsigned long long nww = listed ? (unsigned long long)(*a.tile_count) * (kThreads / 32)
-                                          : (unsigned long long)a.N * wtps;
+    constexpr bool qmode = QMODE;                                         // walk the children of the frontier's survivors
+    const bool listed = !QMODE && a.tile_list != nullptr;                 // walk the survivors of tilecut_kernel
+    if (gate_closed(a)) return;
+    if (qmode && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.counters + 2, a.counters[3]);
+    const unsigned qchunks = (unsigned)((S + 31) / 32);                   // 32-node chunks per depth-(H-2) node
+    const unsigned long long nww = qmode ? (unsigned long long)min(*a.q_count, a.q_cap) * qchunks
+                                   : listed ? (unsigned long long)(*a.tile_count) * (kThreads / 32)
+                                            : (unsigned long long)a.N * wtps;
     const unsigned long long gw = (unsigned long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const unsigned long long GW = (unsigned long long)gridDim.x * (kThreads / 32);
     for (unsigned long long ww = gw; ww < nww; ww += GW) {
-        long long n; unsigned long long wt;
-        if (listed) {
+        long long n; unsigned long long wt = 0, p_q = 0; bool in_q = false;
+        if (qmode) {
+            const unsigned long long e = ww / qchunks;
+            const unsigned c = (unsigned)(ww - e * qchunks) * 32 + lane;
+            const unsigned long long g = a.q_list[e];
+            n = (long long)a.fd[1].div(g);
+            p_q = (g - (unsigned long long)n * a.fd[1].d) * (unsigned long long)S + c;
+            in_q = c < (unsigned)S;
+        } else if (listed) {
             const unsigned long long g = a.tile_list[ww / (kThreads / 32)];
             n = (long long)(g / a.tiles_per_solve);
             wt = (g - (unsigned long long)n * a.tiles_per_solve) * (kThreads / 32) + ww % (kThreads / 32);
@@ -738,10 +873,10 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
         }
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;
-        const unsigned long long tile = wt / (kThreads / 32);
+        const unsigned long long p = qmode ? p_q : a.u_begin + wt * 32 + lane;
+        const bool in_range = qmode ? in_q : p < a.u_end;
+        const unsigned long long tile = in_range ? (p - a.u_begin) / kThreads : 0;       // per lane
         const unsigned seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
-        const unsigned long long p = a.u_begin + wt * 32 + lane;
-        const bool in_range = p < a.u_end;
         ParentRegs pr = {};
         bool near = false, unmoved = false;
         double base = 0.0, base_direct = 0.0, lb = -INFINITY;
@@ -775,7 +910,27 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
 // SMEM: ctl points into shared memory (FULL trees whose {dphi, s} table fits).
 // HT > 0: horizon known at compile time (the walk is fully unrolled, divisors live in uniform registers);
 // HT = 0: run-time horizon a.H.
-template <bool HEAD, int KIND, bool SMEM = false, int HT = 0>
+// fp32 leaf part of the leaf at (xi, eta, psi): the form pass 2 filters with, or (DIRECT) the one pass 1 ranks with
+template <bool HEAD, bool DIRECT>
+__device__ __forceinline__ float leafwalk_score(const SolveParams &P, const ParentRegs &pr, float xi, float eta,
+                                                float psi, float Lsp) {
+    const float g = 3.16227766016837952f * psi;
+    if (DIRECT) {
+        float L = leaf_walk_direct<HEAD>(xi, eta, psi, pr);
+        if ((P.flags & kFlagStartIsOrigin) && xi == 0.f && eta == 0.f)       // the leaf has not moved off the line origin
+            L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
+        return L;
+    }
+    const float r = __fmaf_rn(xi, xi, eta * eta);
+    float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
+                                    : leaf_val<HEAD, false>(xi, eta, r, g, pr);
+    if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
+        L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
+    return L;
+}
+
+// DIRECT: rank with leaf_walk_direct (pass 1); Lsp is then the special-case value in the same units.
+template <bool HEAD, int KIND, bool SMEM = false, int HT = 0, bool DIRECT = false>
 __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveParams &P, const ParentRegs &pr,
                                                const float2 *__restrict__ ctl, unsigned long long j,
                                                float &xi, float &eta, float &psi, float Lsp) {
@@ -797,13 +952,7 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
         xi = __fmaf_rn(t.y, cs, xi);
         eta = __fmaf_rn(t.y, sn, eta);
     }
-    const float r = __fmaf_rn(xi, xi, eta * eta);
-    const float g = 3.16227766016837952f * psi;
-    float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
-                                    : leaf_val<HEAD, false>(xi, eta, r, g, pr);
-    if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
-        L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
-    return L;
+    return leafwalk_score<HEAD, DIRECT>(P, pr, xi, eta, psi, Lsp);
 }
 
 // FULL tree, indices < 2^32, horizon HT known: the control digits of the thread's leaf are kept in registers and
@@ -821,13 +970,7 @@ __device__ __forceinline__ float leafwalk_eval_digits(const SolveParams &P, cons
         xi = __fmaf_rn(t.y, cs, xi);
         eta = __fmaf_rn(t.y, sn, eta);
     }
-    const float r = __fmaf_rn(xi, xi, eta * eta);
-    const float g = 3.16227766016837952f * psi;
-    float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
-                                    : leaf_val<HEAD, false>(xi, eta, r, g, pr);
-    if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
-        L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
-    return L;
+    return leafwalk_score<HEAD, true>(P, pr, xi, eta, psi, Lsp);      // pass 1 only: direct form
 }
 
 // the work loop of one CTA; HT as above
@@ -843,8 +986,13 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;
         ParentRegs pr;
-        const double base = start_as_parent(P, pr);
-        const float Lsp = (float)(P.special - P.e0 * P.e0);     // leaf part of an "on the line origin" leaf
+        double base = start_as_parent(P, pr);
+        double lsp = P.special - P.e0 * P.e0;                   // leaf part of an "on the line origin" leaf
+        if (PASS == 1) {                                        // pass 1 ranks in the direct form: shift both
+            const double off = start_direct_offset(P, pr);
+            base = -off; lsp += off;
+        }
+        const float Lsp = (float)lsp;
         const bool smem = staged && !(P.flags & kFlagSlow);
         const float2 *ctl = smem ? s_ctl : ((P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32);
         const float thr = PASS == 2 ? __double2float_ru(a.tau[n] - base) : 0.f;
@@ -883,8 +1031,8 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
                     const unsigned long long j = j0 + (unsigned)k * kThreads;
                     if (j >= a.u_end) break;
                     float xi, eta, psi;
-                    const float L = smem ? leafwalk_eval<HEAD, KIND, true, HT>(a, P, pr, ctl, j, xi, eta, psi, Lsp)
-                                         : leafwalk_eval<HEAD, KIND, false, HT>(a, P, pr, ctl, j, xi, eta, psi, Lsp);
+                    const float L = smem ? leafwalk_eval<HEAD, KIND, true, HT, PASS == 1>(a, P, pr, ctl, j, xi, eta, psi, Lsp)
+                                         : leafwalk_eval<HEAD, KIND, false, HT, PASS == 1>(a, P, pr, ctl, j, xi, eta, psi, Lsp);
                     if (PASS == 1) best = fminf(best, L);
                     else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
                 }
@@ -922,15 +1070,20 @@ __global__ void __launch_bounds__(kThreads) leafwalk_dump_kernel(const LaunchArg
     const double base = start_as_parent(P, pr);
     const float2 *ctl = (P.flags & kFlagSlow) ? a.g.ctl32_slow : a.g.ctl32;
     const float c0 = (float)cos(P.phi0), s0 = (float)sin(P.phi0);
-    const float Lsp = (float)(P.special - P.e0 * P.e0);
+    const double off = a.dump_direct ? start_direct_offset(P, pr) : 0.0;      // what pass 1 ranks with, in its own units
+    const float Lsp = (float)(P.special - P.e0 * P.e0 + off);
     for (unsigned long long i = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; i < a.dump_count;
          i += (unsigned long long)gridDim.x * kThreads) {
         float xi, eta, psi;
-        const float L = a.mode == 1 ? leafwalk_eval<HEAD, 2>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi, Lsp)
-                                    : leafwalk_eval<HEAD, 0>(a, P, pr, ctl, a.dump_begin + i, xi, eta, psi, Lsp);
+        const unsigned long long j = a.dump_begin + i;
+        const float L = a.dump_direct
+                            ? (a.mode == 1 ? leafwalk_eval<HEAD, 2, false, 0, true>(a, P, pr, ctl, j, xi, eta, psi, Lsp)
+                                           : leafwalk_eval<HEAD, 0, false, 0, true>(a, P, pr, ctl, j, xi, eta, psi, Lsp))
+                            : (a.mode == 1 ? leafwalk_eval<HEAD, 2>(a, P, pr, ctl, j, xi, eta, psi, Lsp)
+                                           : leafwalk_eval<HEAD, 0>(a, P, pr, ctl, j, xi, eta, psi, Lsp));
         a.dump[i] = make_float4((float)P.xs + (c0 * xi - s0 * eta), (float)P.ys + (s0 * xi + c0 * eta),
                                 (float)P.phi0 + psi, L);
-        jrel[i] = base + (double)L;
+        jrel[i] = (a.dump_direct ? -off : base) + (double)L;
     }
 }
 
@@ -1023,6 +1176,14 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
         const double Vmax = kWd * Dmax + E1 * E1 + H1 * H1;
         const double M1 = 3.0 * kWd * Dmax + 2.0 * kWd * smax + 4.0 * E1 * E1 + 3.0 * H1 * H1 + Vmax;
         P.tol1 = fmax(P.tol, 2.0 * M1 * 1.1920928955078125e-07 * tol_scale);
+    } else {
+        // direct form of the leafwalk pass 1 (leaf_walk_direct): the walk's own error (M) plus
+        //   kWd d from dx, dy, their sum of squares and sqrt.approx, the rounding of kWd (u, w)   -> 4 kWd Dmax
+        //   (q + eh)^2, (g + nhh)^2 and the two accumulating FFMAs as above                      -> 4 E1^2 + 3 H1^2 + Vmax
+        const double Dmax = P.d0 + Rtot, E1 = E + Q, H1 = Hh + Gl;
+        const double Vmax = kWd * Dmax + E1 * E1 + H1 * H1;
+        const double M1 = M + 4.0 * kWd * Dmax + 4.0 * E1 * E1 + 3.0 * H1 * H1 + Vmax;
+        P.tol1 = 2.0 * M1 * 1.1920928955078125e-07 * tol_scale;
     }
     P.flags = f; P.pad = 0;
     out[n] = P;
@@ -1157,9 +1318,15 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
         if (pass == 1 && a.prune && a.g.S > kLeafChunk) {
             // big grids (table streamed in chunks): warp-private survivor queues -- config 0: 2.6 s -> 0.25 s per tick
             const size_t smq = sizeof(QEntry) * kWarpQueue * (kThreads / 32);
+            if (a.q_list)
+                return head ? launch_persistent(prefix_pruned_kernel<true, true>, a, pass, smq, sms, st)
+                            : launch_persistent(prefix_pruned_kernel<false, true>, a, pass, smq, sms, st);
             return head ? launch_persistent(prefix_pruned_kernel<true>, a, pass, smq, sms, st)
                         : launch_persistent(prefix_pruned_kernel<false>, a, pass, smq, sms, st);
         }
+        if (pass == 1 && a.prune && a.q_list)
+            return head ? launch_persistent(prefix_kernel<1, true, true, true>, a, pass, sm, sms, st)
+                        : launch_persistent(prefix_kernel<1, false, true, true>, a, pass, sm, sms, st);
         if (pass == 1 && a.prune)   // small grids: nodes are cut lane by lane (the queue costs more than it saves there)
             return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
                         : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
@@ -1183,6 +1350,13 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
     return head ? MPCB_LW_KIND(2, true) : MPCB_LW_KIND(2, false);
 #undef MPCB_LW_KIND
 #undef MPCB_LW
+}
+
+cudaError_t launch_frontier_expand(cudaStream_t st, const LaunchArgs &a, int k, const unsigned long long *src,
+                                   const unsigned *src_count, unsigned long long *dst, unsigned *dst_count,
+                                   unsigned *overflow, int sms) {
+    frontier_expand_kernel<<<sms * 8, kThreads, 0, st>>>(a, k, src, src_count, dst, dst_count, overflow);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tilecut(cudaStream_t st, const LaunchArgs &a, unsigned long long g_begin, unsigned long long g_end,

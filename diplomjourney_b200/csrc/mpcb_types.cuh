@@ -112,13 +112,20 @@ struct LaunchArgs {
     double *bestJ;                         // [N] exact cost of the best candidate so far
     long long *bestIdx;                    // [N]
     int *lock;                             // [N]
-    unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes
+    unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes, [3] same, frontier descent (added to [2] when the descent completes)
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
     // subtree cut (pruned pass 1, H >= 3): tiles that survived the depth-(H-2) bound, as global tile numbers
     // n * tiles_per_solve + tile; null = walk every tile
     const unsigned long long *tile_list;
     const unsigned *tile_count;
+    // frontier descent (pruned pass 1, H >= 3): surviving depth-(H-2) nodes as global ids n * S^(H-2) + index;
+    // pass 1 then walks their children.  q_overflow != 0: a frontier outgrew its list -> the tile path takes over.
+    const unsigned long long *q_list;
+    const unsigned *q_count;
+    unsigned q_cap;
+    const unsigned *q_overflow;
+    int gate;                              // 0 always run, 1 run unless *q_overflow, 2 run only if *q_overflow
     int dump_direct;                       // prefix dump: direct (pass-1) form instead of the pass-2 form
     int npt;                               // depth-(H-1) nodes per thread in the exhaustive prefix pass 1 (1 or 2)
     int i0_begin, i0_end;                   // first-control range of this launch (probe)

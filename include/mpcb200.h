@@ -92,8 +92,12 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * "small_path" (1 = host-API HELD solves with <= 4096 candidates run as one float64 launch, default),
  * "prune" (1 = exact branch-and-bound in the prefix kernel: depth-(H-1) nodes whose children provably cannot
  * reach the refinement window of the best leaf are skipped -- identical results; default 1, 0 = evaluate every leaf),
- * "subtree_cut" (with prune and H >= 3: 256-node tiles below depth-(H-2) nodes whose whole subtree provably cannot
- * reach the window are dropped before any of their nodes is set up -- identical results; default 1),
+ * "subtree_cut" (with prune and H >= 3; identical results in every mode.  1: every 256-node tile is tested against
+ * the bound of its depth-(H-2) node(s) before any of its nodes is set up; fully asynchronous.  3: the frontier of
+ * subtrees that may still hold the argmin is expanded level by level from the root with a bound over all leaves below
+ * each node, and only the children of the depth-(H-2) survivors are ever set up; the call then synchronises the stream
+ * once to read whether a frontier outgrew "frontier_cap" entries (default 2^22), in which case mode 1 redoes pass 1.
+ * 2, default: mode 3 for trees of more than 2^23 tiles per call, mode 1 otherwise.  0: node-level cut only),
  * "nodes_per_thread" (1, 2 or 4, default 2: depth-(H-1) nodes each thread of the exhaustive prefix pass 1 holds --
  * identical results), "dump_direct" (diagnostics: mpcb_dump_leaves_host with MPCB_ALGO_PREFIX returns the cheaper
  * fp32 form the prefix pass 1 ranks with instead of the one pass 2 filters with; default 0). */

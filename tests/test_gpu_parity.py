@@ -268,20 +268,24 @@ def _eps_model(s, origin, H, cost, prefix, smax, dphimax, direct=False):
     if direct:
         d0 = math.hypot(xt - xs, yt - ys)
         Vmax = 1e4 * (d0 + Rtot) + (E + Q) ** 2 + (Hh + Gl) ** 2      # the accumulating FFMAs round at this size
-        M1 = 3 * 1e4 * (d0 + Rtot) + 2 * 1e4 * smax + 4 * (E + Q) ** 2 + 3 * (Hh + Gl) ** 2 + Vmax
-        M = max(M, M1)
+        if prefix:
+            M1 = 3 * 1e4 * (d0 + Rtot) + 2 * 1e4 * smax + 4 * (E + Q) ** 2 + 3 * (Hh + Gl) ** 2 + Vmax
+            M = max(M, M1)
+        else:
+            M = M + 4 * 1e4 * (d0 + Rtot) + 4 * (E + Q) ** 2 + 3 * (Hh + Gl) ** 2 + Vmax
     return M * 2.0 ** -23
 
 
-@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX, "prefix_direct"])
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX, "prefix_direct", "leafwalk_direct"])
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
 def test_fp32_stage_error_stays_inside_the_refinement_window(solver, algo, cost):
     """Every leaf of many small trees (far / near the target / far off the tracked line): the fp32 value the
     kernels compare lies within the per-solve window half-width eps that the refinement pass assumes.
-    "prefix_direct" dumps the values the prefix pass 1 RANKS with (leaf_val_direct) against their own bound tol1/2."""
-    direct = algo == "prefix_direct"
+    "prefix_direct" / "leafwalk_direct" dump the values the two pass-1 kernels RANK with (leaf_val_direct,
+    leaf_walk_direct) against their own bound tol1/2."""
+    direct = algo in ("prefix_direct", "leafwalk_direct")
     if direct:
-        algo = nat.ALGO_PREFIX
+        algo = nat.ALGO_PREFIX if algo == "prefix_direct" else nat.ALGO_LEAFWALK
     solver.set_option("dump_direct", 1 if direct else 0)
     V, B = [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 9)
     solver.set_grid(V, B, L, DT, VMIN)
@@ -307,8 +311,9 @@ def test_fp32_stage_error_stays_inside_the_refinement_window(solver, algo, cost)
 
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
 def test_branch_and_bound_is_exact(solver, cost):
-    """option prune=1 (default) skips depth-(H-1) nodes that provably cannot hold the argmin and, with subtree_cut=1
-    (default, H >= 3), whole 256-node tiles below depth-(H-2) nodes that cannot: the answers must be bit-identical to
+    """option prune=1 (default) skips depth-(H-1) nodes that provably cannot hold the argmin and, with subtree_cut
+    (H >= 3; 1 = per 256-node tile, 3 = frontier descent from the root incl. its overflow fallback, 2 = auto),
+    whole subtrees that cannot: the answers must be bit-identical to
     prune=0 (every leaf evaluated) and to the oracle -- on wide-speed grids where most nodes are cut, on the narrow
     acceleration window where few are, on a deep tree with a tiny grid (a tile straddles many depth-(H-2) nodes) and
     on a grid with S > 1024 restricted to a few first controls (warp-queue kernel walking the survivor list)."""
@@ -329,12 +334,13 @@ def test_branch_and_bound_is_exact(solver, cost):
             assert solver.stats()["pruned_units"] == 0
             solver.set_option("prune", 1)
             pruned = {}
-            for subtree in (0, 1):
+            for subtree, cap in ((0, None), (1, None), (2, None), (3, None), (3, 48)):   # cap 48: a frontier overflows -> tile path
                 solver.set_option("subtree_cut", subtree)
+                solver.set_option("frontier_cap", cap or 2 ** 22)
                 cut = solver.solve(*args, i0_range=i0)
                 st = solver.stats()
-                pruned[subtree] = st["pruned_units"]
-                assert 0 <= st["pruned_units"] <= st["units"] * n
+                pruned[(subtree, cap)] = st["pruned_units"]
+                assert 0 <= st["pruned_units"] <= st["units"] * n, (subtree, cap, st)
                 np.testing.assert_array_equal(cut["index"], full["index"])
                 np.testing.assert_array_equal(cut["cost"], full["cost"])
                 np.testing.assert_array_equal(cut["traj"], full["traj"])
@@ -343,7 +349,8 @@ def test_branch_and_bound_is_exact(solver, cost):
                 if len(V) == 16:
                     assert st["pruned_units"] > 0.2 * st["units"] * n      # v in [0,1]: many nodes cannot win
     finally:
-        solver.set_option("subtree_cut", 1)
+        solver.set_option("subtree_cut", 2)
+        solver.set_option("frontier_cap", 2 ** 22)
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
 

@@ -13,9 +13,9 @@ for grid_name, V, B in (("4x9 v<=1", [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 9)
     vv, bb, dphi = C.control_tables(V, B, L, DT)
     smax, dphimax = float(np.max(vv) * DT), float(np.max(np.abs(dphi)))
     sc = C.random_scenarios(40, 123)
-    for algo_name in ("leafwalk", "prefix", "prefix_direct"):
-        algo = nat.ALGO_LEAFWALK if algo_name == "leafwalk" else nat.ALGO_PREFIX
-        direct = algo_name == "prefix_direct"          # the form the prefix pass 1 ranks with, against tol1/2
+    for algo_name in ("leafwalk", "leafwalk_direct", "prefix", "prefix_direct"):
+        algo = nat.ALGO_LEAFWALK if algo_name.startswith("leafwalk") else nat.ALGO_PREFIX
+        direct = algo_name.endswith("_direct")         # the forms the pass-1 kernels rank with, against tol1/2
         s.set_option("dump_direct", 1 if direct else 0)
         for cost in (C.COST_MM, C.COST_TREE):
             worst = {}
@@ -28,5 +28,5 @@ for grid_name, V, B in (("4x9 v<=1", [0.0, 0.3, 0.6, 1.0], np.linspace(-1, 1, 9)
                     ok = Jo < 1e7
                     eps = _eps_model(st, og, 3, cost, algo == nat.ALGO_PREFIX, smax, dphimax, direct)
                     worst[name] = max(worst.get(name, 0.0), float(np.abs(J - Jo)[ok].max() / eps))
-            print(f"{grid_name:12s} algo={algo_name:13s} cost={cost:4s} worst |err|/eps: " +
+            print(f"{grid_name:12s} algo={algo_name:15s} cost={cost:4s} worst |err|/eps: " +
                   "  ".join(f"{k}={v:.3f}" for k, v in worst.items()))
