@@ -197,6 +197,11 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
         unsigned long long r = kThreads;
         for (int k = H - 1; k >= 0; --k) { a.step_digits[k] = mode == MPCB_MODE_FULL ? (unsigned)(r % S) : 0u; r = mode == MPCB_MODE_FULL ? r / S : 0; }
     }
+    for (int i = 0; i < kMaxH; ++i) {   // heading range after i+1 steps, for the pruning bounds
+        const double ang = (i + 1) * h->g.dphimax;
+        a.cosk[i] = ang < 3.141592653589793 ? std::cos(ang) : -2.0;
+        a.sink[i] = ang < 3.141592653589793 ? std::sin(ang) : 0.0;
+    }
     a.tile_units = pl.prefix ? kThreads : kThreads * kLeafPerThread;
     a.lw_smem = (!pl.prefix && mode == MPCB_MODE_FULL && h->g.S <= 4096) ? 1 : 0;
 }
@@ -217,7 +222,7 @@ static int ensure_tables(mpcb_handle *h) {
     double vmin_grid = v[0];
     for (int i = 1; i < nv; ++i) vmin_grid = std::min(vmin_grid, v[i]);
     const double v_slow = vmin_grid > v_min ? vmin_grid : v_min;   // math_model_tree.py:312-316
-    double smax = 0, dphimax = 0;
+    double smax = 0, dphimax = 0, smin = INFINITY;
     for (int iv = 0; iv < nv; ++iv)
         for (int ib = 0; ib < nb; ++ib) {
             const int c = iv * nb + ib;
@@ -227,6 +232,7 @@ static int ensure_tables(mpcb_handle *h) {
                 const double s = vc * delta_t;
                 const double cd = std::cos(dphi), sd = std::sin(dphi);
                 smax = std::max(smax, std::fabs(s));
+                smin = std::min(smin, s);
                 dphimax = std::max(dphimax, std::fabs(dphi));
                 if (variant == 0) {
                     t64[c] = make_double4(cd, sd, s, dphi);
@@ -274,7 +280,7 @@ static int ensure_tables(mpcb_handle *h) {
     g.leaf32 = h->leaf32.as<float4>();
     g.leaf32p = h->leaf32p.as<float4>();
     g.ctl32 = h->ctl32.as<float2>(); g.ctl32_slow = h->ctl32_slow.as<float2>();
-    g.S = S; g.nb = nb; g.dt = delta_t; g.smax = smax; g.dphimax = dphimax;
+    g.S = S; g.nb = nb; g.dt = delta_t; g.smax = smax; g.dphimax = dphimax; g.smin = smin;
     h->tables_ready = true;
     return MPCB_OK;
 }

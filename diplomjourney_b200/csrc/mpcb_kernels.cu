@@ -183,18 +183,38 @@ __device__ __forceinline__ void walk_step(const double4 t, double &xi, double &e
     psi += t.w;
 }
 
-// Lower bound of J_rel over every leaf that lies `steps` further control steps below a node at (xi, eta, psi):
-// straight at the target all the way (d >= D - steps s_max, triangle inequality) plus the most favourable line
-// and heading offsets (|q| <= wl steps s_max, |g| <= wh steps dphi_max).
+// How far `steps` further control steps can bring a node towards the target, at most.  The distance of a leaf is at
+// least its projection on the node's bearing to the target: d >= D - sum_i s_i cos(theta_i), theta_i the angle between
+// the heading after step i and that bearing.  After i steps the heading has turned by at most i dphi_max, so
+// theta_i >= max(0, gap - i dphi_max) with gap the present angle between heading and bearing; and s_i lies in
+// [s_min, s_max].  (rx, ry) is the target relative to the node, (ch, sh) the node's heading, same frame.
+// A robot that faces away from its target, or cannot stop, is thereby known to move AWAY from it.
+// Grids with negative speeds fall back to the isotropic bound steps * max|s|.
+__device__ __forceinline__ double reach_towards_target(const LaunchArgs &a, double rx, double ry, double D, double ch,
+                                                       double sh, int steps) {
+    if (a.g.smin < 0.0 || !(D > 0.0)) return steps * a.g.smax;
+    const double inv = 1.0 / D;
+    const double cg = (rx * ch + ry * sh) * inv, sg = fabs(rx * sh - ry * ch) * inv;     // cos, sin of the gap
+    double r = 0.0;
+    for (int i = 0; i < steps; ++i) {
+        const double cm = cg >= a.cosk[i] ? 1.0 : cg * a.cosk[i] + sg * a.sink[i];       // cos(max(0, gap - (i+1) dphi_max))
+        r += cm >= 0.0 ? a.g.smax * cm : a.g.smin * cm;
+    }
+    return r;
+}
+
+// Lower bound of J_rel over every leaf that lies `steps` further control steps below a node at (xi, eta, psi) with
+// heading (cp, sp): the closest approach to the target that the steering limits allow (reach_towards_target) plus
+// the most favourable line and heading offsets (|q| <= wl steps s_max, |g| <= wh steps dphi_max).
 __device__ __forceinline__ double subtree_lower_bound(const LaunchArgs &a, const SolveParams &P, double xi, double eta,
-                                                      double psi, int steps) {
+                                                      double psi, double cp, double sp, int steps) {
     const double relx = P.u0 - xi, rely = P.w0 - eta;
     const double D = sqrt(relx * relx + rely * rely);
     const double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
     const double hp = P.hp0 - P.wh * psi;
     const double base0 = kWd * (D - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
-    const double reach = steps * a.g.smax;
-    return base0 - kWd * reach + quad_min(2.0 * ep, P.wl * reach) + quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
+    return base0 - kWd * reach_towards_target(a, relx, rely, D, cp, sp, steps) +
+           quad_min(2.0 * ep, P.wl * steps * a.g.smax) + quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
 }
 
 __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
@@ -223,7 +243,7 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     near = !(Dp >= 4.0 * a.g.smax);
     // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
     const double base0 = kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
-    // no child can do better than: one step straight at the target (d >= Dp - s_max, triangle inequality)
+    // no child can do better than: one step as straight at the target as the steering allows (reach_towards_target)
     // plus the most favourable line and heading offsets  (|q| <= wl s_max, |g| <= wh dphi_max)
     if (base_direct) {
         pr.eh = 0.5f * pr.e2; pr.nhh = -0.5f * pr.h2;
@@ -231,8 +251,9 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
         pr.D2s = (float)(kWd * kWd * (Dp * Dp));
         *base_direct = base0 - kWd * Dp - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
     }
-    if (lower_bound)
-        *lower_bound = base0 - kWd * a.g.smax + quad_min(2.0 * ep, P.wl * a.g.smax) + quad_min(-2.0 * hp, P.wh * a.g.dphimax);
+    if (lower_bound)   // in the node's own frame the heading is (1, 0) and the target (u, w)
+        *lower_bound = base0 - kWd * reach_towards_target(a, u, w, Dp, 1.0, 0.0, 1) + quad_min(2.0 * ep, P.wl * a.g.smax) +
+                       quad_min(-2.0 * hp, P.wh * a.g.dphimax);
     return base0 + (near ? dp_rem : 0.0);
 }
 
@@ -726,7 +747,7 @@ __global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchA
                     walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
                 }
                 const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
-                keep = !(subtree_lower_bound(a, P, xi, eta, psi, steps) > bound);      // NaN bounds never cut
+                keep = !(subtree_lower_bound(a, P, xi, eta, psi, cp, sp, steps) > bound);      // NaN bounds never cut
                 if (!keep) cut += below;
             }
         }
@@ -776,7 +797,7 @@ __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, u
                     rem -= i * a.fd[k + 2].d;
                     walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
                 }
-                keep = !(subtree_lower_bound(a, P, xi, eta, psi, 2) > bound);      // NaN bounds never cut
+                keep = !(subtree_lower_bound(a, P, xi, eta, psi, cp, sp, 2) > bound);      // NaN bounds never cut
             }
             if (!keep) cut_nodes = (unsigned)(p_hi - p_lo);
         }

@@ -66,7 +66,8 @@ struct GridTables {
     const float2 *ctl32_slow;
     int S, nb;
     double dt;
-    double smax, dphimax;       // max s_c, max |dphi_c| (both variants) -- error model
+    double smax, dphimax;       // max |s_c|, max |dphi_c| (both variants) -- error model, pruning bounds
+    double smin;                // min s_c (both variants) -- pruning bounds
 };
 
 // Per solve (float64). Built by prep_kernel from the raw inputs.
@@ -115,6 +116,7 @@ struct LaunchArgs {
     unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes, [3] same, frontier descent (added to [2] when the descent completes)
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
+    double cosk[kMaxH], sink[kMaxH];       // cos / sin of (i+1) dphi_max: the heading range reachable in i+1 steps (cos = -2: the whole circle)
     // subtree cut (pruned pass 1, H >= 3): tiles that survived the depth-(H-2) bound, as global tile numbers
     // n * tiles_per_solve + tile; null = walk every tile
     const unsigned long long *tile_list;
