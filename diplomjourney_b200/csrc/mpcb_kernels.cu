@@ -379,11 +379,9 @@ __device__ __forceinline__ void publish_segmin_lanes(const LaunchArgs &a, unsign
     else if (v < INFINITY) atomicMin(reinterpret_cast<unsigned long long *>(a.segmin) + seg, ordered_key(v));
 }
 
-// gated launches: the frontier path and its tile-path fallback are both enqueued; one of them returns at once
+// frontier mode: pass 1 must not walk a list that a frontier outgrew (the host then redoes it through the tile bound)
 __device__ __forceinline__ bool gate_closed(const LaunchArgs &a) {
-    if (a.gate == 0) return false;
-    const bool overflow = *(volatile const unsigned *)a.q_overflow != 0;
-    return a.gate == 1 ? overflow : !overflow;
+    return a.gate != 0 && *(volatile const unsigned *)a.q_overflow != 0;
 }
 
 // work item -> (segment, solve, tile range).  PASS 1 walks all segments, PASS 2 the work list.
@@ -709,8 +707,8 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
 // H-k-1 steps below it against the solve's running upper bound -- until depth H-2; pass 1 then sets up and scores
 // only the children of those survivors.  Cut subtrees are never enumerated at all, which is what makes 1e15-leaf
 // trees a matter of milliseconds when the bound bites.  Node ids are global: n * S^k + index, so a child is simply
-// id * S + c.  The lists have a fixed capacity; a frontier that outgrows it raises *overflow and the (already
-// enqueued, gated) tile path does the solve instead -- no host round trip either way.
+// id * S + c.  The lists have a fixed capacity; a frontier that outgrows it raises *overflow, the remaining levels and
+// pass 1 return at once, and the host (which reads that one flag) redoes pass 1 through the tile bound.
 __global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchArgs a, int k,
                                                                    const unsigned long long *__restrict__ src,
                                                                    const unsigned *src_count,
@@ -776,7 +774,6 @@ __global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchA
 __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, unsigned long long g_begin,
                                                            unsigned long long g_end, unsigned long long *list,
                                                            unsigned *count) {
-    if (gate_closed(a)) return;
     const unsigned long long g = g_begin + blockIdx.x * (unsigned long long)kThreads + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     bool keep = false;

@@ -127,7 +127,7 @@ struct LaunchArgs {
     const unsigned *q_count;
     unsigned q_cap;
     const unsigned *q_overflow;
-    int gate;                              // 0 always run, 1 run unless *q_overflow, 2 run only if *q_overflow
+    int gate;                              // 1: pass 1 returns at once if *q_overflow (frontier mode)
     int dump_direct;                       // prefix dump: direct (pass-1) form instead of the pass-2 form
     int npt;                               // depth-(H-1) nodes per thread in the exhaustive prefix pass 1 (1 or 2)
     int i0_begin, i0_end;                   // first-control range of this launch (probe)

@@ -355,6 +355,41 @@ def test_branch_and_bound_is_exact(solver, cost):
         solver.set_option("algo", nat.ALGO_AUTO)
 
 
+def test_branch_and_bound_random_sweep(solver):
+    """A few hundred random scenarios per grid -- robots facing away from, next to and far from their targets, robots off
+    the tracked line, a grid that cannot stop, one that starts from rest, one with reverse speeds -- solved exhaustively
+    and with both subtree-cut modes: bit-identical records (tools/prune_sweep.py is the long version)."""
+    n = 128
+    cases = [(C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0), 3),
+             (np.linspace(0, 1, 16), np.linspace(-np.radians(60), np.radians(60), 16), 3),
+             (np.linspace(0.1, 1, 7), np.linspace(-1.4, 1.4, 9), 4),
+             (np.linspace(-0.5, 1, 5), np.linspace(-1, 1, 5), 5)]
+    solver.set_option("algo", nat.ALGO_PREFIX)
+    try:
+        for ci, (V, B, H) in enumerate(cases):
+            solver.set_grid(V, B, L, DT, VMIN)
+            sc = C.random_scenarios(n, 2000 + ci)
+            k = n // 8
+            sc[:k, 3:5] = sc[:k, :2] + np.random.default_rng(ci).uniform(-0.1, 0.1, (k, 2))
+            sc[k:2 * k, 3:5] = sc[k:2 * k, :2] + np.random.default_rng(ci + 50).uniform(-300, 300, (k, 2))
+            origin = sc[:, :2].copy()
+            origin[2 * k:3 * k] += np.random.default_rng(ci + 99).uniform(-5, 5, (k, 2))
+            for cost in (nat.COST_MM, nat.COST_TREE):
+                args = (nat.MODE_FULL, cost, H, sc[:, :3], sc[:, 3:5], origin)
+                solver.set_option("prune", 0)
+                ref = solver.solve(*args)
+                solver.set_option("prune", 1)
+                for mode in (1, 3):
+                    solver.set_option("subtree_cut", mode)
+                    cut = solver.solve(*args)
+                    for key in ("index", "cost", "traj", "first_control"):
+                        np.testing.assert_array_equal(cut[key], ref[key], err_msg=f"case {ci} cost {cost} mode {mode} {key}")
+    finally:
+        solver.set_option("subtree_cut", 2)
+        solver.set_option("prune", 1)
+        solver.set_option("algo", nat.ALGO_AUTO)
+
+
 def test_slow_flag_is_held_only(solver):
     """MPCB_FLAG_SLOW is the online controller's override; a FULL solve must ignore it (both algorithms)."""
     V, B = [0.2, 0.6, 1.0], np.linspace(-1, 1, 5)
