@@ -181,6 +181,33 @@ def held_metrics(solver, nat, C, device_index):
     return out
 
 
+def bigtree_metrics(solver, nat):
+    """BASELINE configs[2] and configs[4]: ONE oversized FULL tree (config.py scenario) on this GPU through the host API
+    with the exact branch-and-bound -- the only way such a tree is solved in finite time; `exhaustive_s` is the same
+    tree at the measured every-leaf rate of the headline kernel (profiles/r1i_config3.txt, r1g_multigpu.txt)."""
+    from diplomjourney_b200 import config as cfg
+    out = {}
+    solver.set_option("prune", 1)
+    for name, H, n, exhaustive_s in (("configs[2] H=5 32x32", 5, 32, 364.0), ("configs[4] H=6 16x16", 6, 16, 19.2 * 8)):
+        V = np.linspace(0.0, cfg.v_max, n)
+        B = np.linspace(-cfg.beta_max, cfg.beta_max, n)
+        solver.set_grid(V, B, cfg.L, cfg.delta_t, cfg.v_min)
+        st, tg, og = (cfg.x_0, cfg.y_0, cfg.phi_0), (cfg.x_t, cfg.y_t), (cfg.x_0, cfg.y_0)
+        best = None
+        for _ in range(3):
+            t = time.perf_counter()
+            r = solver.solve(nat.MODE_FULL, nat.COST_MM, H, st, tg, og)
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+        stt = solver.stats()
+        out[name] = dict(leaves=int(stt["leaves_per_solve"]), seconds=best, solves_per_s=1.0 / best,
+                         leaf=int(r["index"][0]), cost=float(r["cost"][0]),
+                         nodes_set_up=int(stt["units"] - stt["pruned_units"]), nodes=int(stt["units"]),
+                         exhaustive_seconds_one_gpu=exhaustive_s)
+    solver.set_option("prune", 0)
+    return out
+
+
 def run_reference(args):
     wl = workload(args.workload)
     rank = int(os.environ.get("RANK", "0"))
@@ -340,13 +367,15 @@ def run_gpu(args):
         parents = pst["units"] * n
         pruned = dict(ms_per_step=float(tp[0]) / args.steps, solves_per_s=n * world * args.steps / (float(tp[0]) * 1e-3),
                       evaluated_fraction=1.0 - pst["pruned_units"] / max(parents, 1), same_leaves_as_unpruned=same,
-                      note="option prune=1: depth-(H-1) nodes whose children provably cannot reach the refinement "
-                           "window are skipped; `value` above is measured with prune=0 (every leaf evaluated)")
+                      note="option prune=1 (the library default): exact branch-and-bound -- nodes and subtrees whose leaves "
+                           "provably cannot reach the refinement window are skipped, identical records; `value` above "
+                           "is measured with prune=0 (every leaf evaluated)")
         if not same:
             raise SystemExit("PARITY FAILURE in bench: pruned and unpruned solves disagree")
         solver.set_option("prune", 0)
     solver.set_option("algo", nat.ALGO_AUTO)
     held = held_metrics(solver, nat, C, local) if rank == 0 and args.algo == "auto" else None
+    bigtree = bigtree_metrics(solver, nat) if rank == 0 and args.algo == "auto" else None
     if rank == 0:
         pk = peaks()
         clk_hz = pk["sm_max_mhz"] * 1e6
@@ -381,7 +410,7 @@ def run_gpu(args):
             e2e=dict(value=e2e_value, unit="rollouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      solves_per_s=n * world * args.steps / float(te[0])),
             gpu_launches=stats["kernel_launches"] * args.steps,
-            clocks=clocks, parity=parity, held=held, pruned=pruned,
+            clocks=clocks, parity=parity, held=held, pruned=pruned, bigtree=bigtree,
             refine=dict(segments=stats["refine_segments"], candidates=stats["refine_candidates"]),
         )
         if world == 1 and not args.no_cpu:

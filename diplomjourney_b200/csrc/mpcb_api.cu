@@ -19,6 +19,8 @@ cudaError_t launch_prep(cudaStream_t, long long, const double *, const double *,
                         const uint8_t *, int, int, int, double, double, double, SolveParams *);
 cudaError_t launch_pass(cudaStream_t, const LaunchArgs &, int pass, bool prefix, int sms);
 cudaError_t launch_reduce_compact(cudaStream_t, const LaunchArgs &, double *, unsigned *, unsigned *, int sms);
+cudaError_t launch_reduce_compact_wide(cudaStream_t, const LaunchArgs &, double *, unsigned *, unsigned *, void *scratch,
+                                       int sms, int *launches);
 cudaError_t launch_probe(cudaStream_t, const LaunchArgs &, int sms);
 cudaError_t launch_tilecut(cudaStream_t, const LaunchArgs &, unsigned long long g_begin, unsigned long long g_end,
                            unsigned long long *list, unsigned *count);
@@ -54,6 +56,7 @@ struct DevBuf {
 
 constexpr unsigned long long kSegCap = 1ULL << 22;
 constexpr unsigned long long kTileBatch = 1ULL << 23;   // subtree cut: tiles per batch (survivor list <= 64 MiB)
+constexpr unsigned long long kWideReduceSegs = 1ULL << 15; // segments per solve from which the per-solve reduction runs grid-wide
 constexpr unsigned long long kFrontierCap = 1ULL << 22; // frontier descent: entries per list (two lists = the tile list's 64 MiB)
 
 void fastdiv32_init(FastDiv32 &f, unsigned long long d64) {
@@ -99,7 +102,7 @@ struct mpcb_handle_s {
     int subtree_cut = 2;       // pruned pass 1, H >= 3: 0 off, 1 depth-(H-2) bound per 256-node tile, 2 auto (frontier descent from the root for trees of more than one tile batch), 3 frontier always
     int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
-    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list;
+    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list, reduce_scratch;
     DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
     DevBuf loop_log, loop_ticks, loop_status, small_in, small_out, fl_last, fl_k, fl_have, fl_flags, fl_count;
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
@@ -320,7 +323,7 @@ int mpcb_destroy(mpcb_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
-                      &h->lock, &h->ub, &h->tile_list, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
+                      &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
                       &h->loop_status, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
                       &h->fl_count})
@@ -504,7 +507,13 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     } else if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
     }
-    CK(launch_reduce_compact(h->stream, a, h->tau.as<double>(), h->worklist.as<unsigned>(), work_count, h->sms)); ++launches;
+    if (a.segs_per_solve >= kWideReduceSegs) {   // few solves with many segments each: reduce and compact grid-wide
+        CK(h->reduce_scratch.ensure(2 * sizeof(double) * N));
+        CK(launch_reduce_compact_wide(h->stream, a, h->tau.as<double>(), h->worklist.as<unsigned>(), work_count,
+                                      h->reduce_scratch.p, h->sms, &launches));
+    } else {
+        CK(launch_reduce_compact(h->stream, a, h->tau.as<double>(), h->worklist.as<unsigned>(), work_count, h->sms)); ++launches;
+    }
     if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 2, pl.prefix, h->sms)); ++launches;
     }

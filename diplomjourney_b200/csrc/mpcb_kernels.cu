@@ -1263,6 +1263,63 @@ __global__ void __launch_bounds__(kThreads) reduce_compact_kernel(const LaunchAr
     }
 }
 
+// The same in three grid-wide steps, for launches whose solves have many segments each (one oversized tree: 4e6
+// segments scanned by ONE CTA took 5.8 of the 6.0 ms of a 1e15-leaf pruned solve):
+//   (1) every CTA folds the minimum of a chunk of segment keys into its solve's key,
+//   (2) one thread per solve turns that into the window edge and resets the solve's record,
+//   (3) every CTA lists the qualifying segments of a chunk (warp-aggregated append; the order of the work list is
+//       irrelevant -- pass 2 reduces lexicographically).
+constexpr unsigned kReduceChunk = 4096;      // segment keys per CTA step
+
+__global__ void __launch_bounds__(kThreads) segmin_fold_kernel(const LaunchArgs a, unsigned long long *solve_key) {
+    const unsigned sps = (unsigned)a.segs_per_solve;
+    const unsigned cps = (sps + kReduceChunk - 1) / kReduceChunk;          // chunks per solve
+    const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(a.segmin);
+    for (unsigned long long w = blockIdx.x; w < (unsigned long long)a.N * cps; w += gridDim.x) {
+        const unsigned long long n = w / cps;
+        const unsigned lo = (unsigned)(w - n * cps) * kReduceChunk, hi = min(lo + kReduceChunk, sps);
+        unsigned long long k = ~0ULL;
+        for (unsigned i = lo + threadIdx.x; i < hi; i += kThreads) k = min(k, keys[n * sps + i]);
+        for (int o = 16; o > 0; o >>= 1) k = min(k, __shfl_xor_sync(0xffffffffu, k, o));
+        if ((threadIdx.x & 31) == 0 && k != ~0ULL) atomicMin(solve_key + n, k);
+    }
+}
+
+__global__ void window_edge_kernel(const LaunchArgs a, const unsigned long long *solve_key, double *tau, double *tau1) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    const double v = ordered_value(solve_key[n]);                           // untouched key (all ones) -> NaN/inf: no segment
+    const bool any = solve_key[n] != ~0ULL;
+    tau1[n] = any ? v + a.sp[n].tol1 : -INFINITY;
+    tau[n] = any ? v + 0.5 * (a.sp[n].tol1 + a.sp[n].tol) : -INFINITY;
+    a.bestJ[n] = INFINITY;
+    a.bestIdx[n] = -1;
+    a.lock[n] = 0;
+}
+
+__global__ void __launch_bounds__(kThreads) seg_compact_kernel(const LaunchArgs a, const double *tau1, unsigned *worklist,
+                                                               unsigned *work_count) {
+    const unsigned sps = (unsigned)a.segs_per_solve;
+    const unsigned cps = (sps + kReduceChunk - 1) / kReduceChunk;
+    const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(a.segmin);
+    const unsigned lane = threadIdx.x & 31u;
+    for (unsigned long long w = blockIdx.x; w < (unsigned long long)a.N * cps; w += gridDim.x) {
+        const unsigned long long n = w / cps;
+        const unsigned lo = (unsigned)(w - n * cps) * kReduceChunk, hi = min(lo + kReduceChunk, sps);
+        const double t = tau1[n];
+        for (unsigned i0 = lo + (threadIdx.x & ~31u); i0 < hi; i0 += kThreads) {
+            const unsigned i = i0 + lane;
+            const bool take = i < hi && ordered_value(keys[n * sps + i]) <= t;
+            const unsigned mk = __ballot_sync(0xffffffffu, take);
+            if (!mk) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(work_count, (unsigned)__popc(mk));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) worklist[base + __popc(mk & ((1u << lane) - 1u))] = (unsigned)(n * sps + i);
+        }
+    }
+}
+
 // Winner -> outputs: float64 re-roll of its trajectory, threshold test (math_model.py:195).
 __global__ void finalize_kernel(const LaunchArgs a, double *best_cost, long long *best_index, double *best_traj,
                                 double *first_control) {
@@ -1393,6 +1450,22 @@ cudaError_t launch_reduce_compact(cudaStream_t st, const LaunchArgs &a, double *
                                   unsigned *work_count, int sms) {
     reduce_compact_kernel<<<grid_for((unsigned long long)a.N, sms, 8), kThreads, 0, st>>>(a, tau, worklist,
                                                                                          work_count);
+    return cudaGetLastError();
+}
+
+// the grid-wide flavour; scratch = 2 * N 8-byte words (solve keys, pass-1 window edges)
+cudaError_t launch_reduce_compact_wide(cudaStream_t st, const LaunchArgs &a, double *tau, unsigned *worklist,
+                                       unsigned *work_count, void *scratch, int sms, int *launches) {
+    unsigned long long *solve_key = static_cast<unsigned long long *>(scratch);
+    double *tau1 = reinterpret_cast<double *>(solve_key + a.N);
+    cudaError_t e = cudaMemsetAsync(solve_key, 0xFF, sizeof(unsigned long long) * a.N, st);
+    if (e != cudaSuccess) return e;
+    const unsigned long long chunks = (unsigned long long)a.N * ((a.segs_per_solve + kReduceChunk - 1) / kReduceChunk);
+    const int grid = grid_for(chunks, sms, 8);
+    segmin_fold_kernel<<<grid, kThreads, 0, st>>>(a, solve_key);
+    window_edge_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a, solve_key, tau, tau1);
+    seg_compact_kernel<<<grid, kThreads, 0, st>>>(a, tau1, worklist, work_count);
+    *launches += 3;
     return cudaGetLastError();
 }
 

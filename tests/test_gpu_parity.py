@@ -390,6 +390,24 @@ def test_branch_and_bound_random_sweep(solver):
         solver.set_option("algo", nat.ALGO_AUTO)
 
 
+def test_many_segments_per_solve(solver):
+    """One solve with 65,536 segments (H=4 on the 16x16 grid, 4.3e9 leaves): from 32,768 segments per solve on, the
+    per-solve reduction of the segment minima and the compaction of the work list run grid-wide instead of on one
+    CTA per solve.  Exhaustive and pruned against the C oracle."""
+    V, B = np.linspace(0.0, 1.0, 16), np.linspace(-np.radians(60), np.radians(60), 16)
+    solver.set_grid(V, B, L, DT, VMIN)
+    s = C.random_scenarios(1, 4242)[0]
+    o = K.solve_full(s[:3], s[3:], s[:2], V, B, 4, C.COST_MM)
+    try:
+        for prune in (0, 1):
+            solver.set_option("prune", prune)
+            r = solver.solve(nat.MODE_FULL, nat.COST_MM, 4, s[:3], s[3:5], s[:2])
+            assert solver.stats()["segments"] == 65536
+            _check(r, 0, o, 4)
+    finally:
+        solver.set_option("prune", 1)
+
+
 def test_slow_flag_is_held_only(solver):
     """MPCB_FLAG_SLOW is the online controller's override; a FULL solve must ignore it (both algorithms)."""
     V, B = [0.2, 0.6, 1.0], np.linspace(-1, 1, 5)

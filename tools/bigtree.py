@@ -27,7 +27,7 @@ def run(label, subtree, i0_range=None):
     dt = time.perf_counter() - t
     st = s.stats()
     leaves = st["leaves_per_solve"]
-    print(f"bigtree H={H} S={S} phi0={phi0:g} {label}: leaves={leaves:.4e} time={dt:.3f}s effective {leaves/dt:.3e} rollouts/s "
+    print(f"bigtree H={H} S={S} phi0={phi0:g} {label}: leaves={leaves:.4e} time={dt*1e3:.3f} ms effective {leaves/dt:.3e} rollouts/s "
           f"leaf={int(r['index'][0])} cost={r['cost'][0]:.6f} first_control={r['first_control'][0].tolist()} "
           f"pruned_nodes={st['pruned_units']}/{st['units']} launches={st['kernel_launches']} "
           f"refine(seg={st['refine_segments']},cand={st['refine_candidates']})", flush=True)

@@ -13,7 +13,7 @@ for tick in (1, 2):     # tick 1 includes the one-off table build/upload and laz
     r = rm.predictive_control(*state, rm.x_t, rm.y_t)
     dt = time.perf_counter() - t
     st = _native.default_solver().stats()
-    print(f"config0 prune={int(prune)} tick {tick}: S={rm.size_max_1} leaves={rm.size_max_3} time={dt:.2f}s "
+    print(f"config0 prune={int(prune)} tick {tick}: S={rm.size_max_1} leaves={rm.size_max_3} time={dt*1e3:.1f} ms "
           f"rate={rm.size_max_3/dt:.3e} rollouts/s result={[float(x) for x in r]} leaf={rm.last_leaf_index} "
           f"criterion={rm.optimal_criterion:.6f} stats={st}")
     state = (r[0], r[1], r[2], r[3])
