@@ -18,6 +18,13 @@
 //             loop over the S children with the per-control displacement table in shared
 //             memory (no MUFU sin/cos in the inner loop: the child pose is a rotation of a
 //             tabulated displacement into the parent frame)
+// Pass 1 of either only RANKS (cheaper "direct" forms under their own error bound tol1, leaf_val_direct /
+// leaf_walk_direct); pass 2 filters with the accurate offset form before the float64 re-evaluation.
+//
+// Exact branch-and-bound (option prune): lower bounds on the cost of every leaf below a
+// node (reach_towards_target, subtree_lower_bound) against a running upper bound cut nodes in pass 1, 256-node
+// tiles before pass 1 (tilecut_kernel) or whole subtrees from the root down (frontier_expand_kernel); the
+// records returned are bit-identical to evaluating every leaf.
 #include "mpcb_types.cuh"
 
 #ifndef MPCB_UNROLL2

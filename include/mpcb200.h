@@ -91,7 +91,9 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * "refine" (1 = float64 re-evaluation of near-minimal leaves, default; 0 = fp32 winner),
  * "small_path" (1 = host-API HELD solves with <= 4096 candidates run as one float64 launch, default),
  * "prune" (1 = exact branch-and-bound in the prefix kernel: depth-(H-1) nodes whose children provably cannot
- * reach the refinement window of the best leaf are skipped -- identical results; default 1, 0 = evaluate every leaf),
+ * reach the refinement window of the best leaf are skipped -- a lower bound from the distance to the target, the
+ * steering and speed limits and the most favourable line / heading offsets against the best cost found so far;
+ * identical results; default 1, 0 = evaluate every leaf as the reference does),
  * "subtree_cut" (with prune and H >= 3; identical results in every mode.  1: every 256-node tile is tested against
  * the bound of its depth-(H-2) node(s) before any of its nodes is set up; fully asynchronous.  3: the frontier of
  * subtrees that may still hold the argmin is expanded level by level from the root with a bound over all leaves below
@@ -99,8 +101,8 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * once to read whether a frontier outgrew "frontier_cap" entries (default 2^22), in which case mode 1 redoes pass 1.
  * 2, default: mode 3 for trees of more than 2^23 tiles per call, mode 1 otherwise.  0: node-level cut only),
  * "nodes_per_thread" (1, 2 or 4, default 2: depth-(H-1) nodes each thread of the exhaustive prefix pass 1 holds --
- * identical results), "dump_direct" (diagnostics: mpcb_dump_leaves_host with MPCB_ALGO_PREFIX returns the cheaper
- * fp32 form the prefix pass 1 ranks with instead of the one pass 2 filters with; default 0). */
+ * identical results), "dump_direct" (diagnostics: mpcb_dump_leaves_host returns the cheaper fp32 form pass 1 ranks
+ * with instead of the one pass 2 filters with; default 0), "frontier_cap" (see "subtree_cut"). */
 MPCB_API int mpcb_set_option(mpcb_handle *h, const char *name, double value);
 
 /* Batch of N independent MPC solves sharing the grid.  Replaces N calls of
