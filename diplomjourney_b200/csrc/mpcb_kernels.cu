@@ -22,7 +22,7 @@
 // leaf_walk_direct); pass 2 filters with the accurate offset form before the float64 re-evaluation.
 //
 // Exact branch-and-bound (option prune): lower bounds on the cost of every leaf below a
-// node (reach_towards_target, subtree_lower_bound) against a running upper bound cut nodes in pass 1, 256-node
+// node (projection_range, lower_bound_from, subtree_lower_bound) against a running upper bound cut nodes in pass 1, 256-node
 // tiles before pass 1 (tilecut_kernel) or whole subtrees from the root down (frontier_expand_kernel); the
 // records returned are bit-identical to evaluating every leaf.
 #include "mpcb_types.cuh"
@@ -190,29 +190,55 @@ __device__ __forceinline__ void walk_step(const double4 t, double &xi, double &e
     psi += t.w;
 }
 
-// How far `steps` further control steps can bring a node towards the target, at most.  The distance of a leaf is at
-// least its projection on the node's bearing to the target: d >= D - sum_i s_i cos(theta_i), theta_i the angle between
-// the heading after step i and that bearing.  After i steps the heading has turned by at most i dphi_max, so
-// theta_i >= max(0, gap - i dphi_max) with gap the present angle between heading and bearing; and s_i lies in
-// [s_min, s_max].  (rx, ry) is the target relative to the node, (ch, sh) the node's heading, same frame.
-// A robot that faces away from its target, or cannot stop, is thereby known to move AWAY from it.
-// Grids with negative speeds fall back to the isotropic bound steps * max|s|.
-__device__ __forceinline__ double reach_towards_target(const LaunchArgs &a, double rx, double ry, double D, double ch,
-                                                       double sh, int steps) {
-    if (a.g.smin < 0.0 || !(D > 0.0)) return steps * a.g.smax;
-    const double inv = 1.0 / D;
-    const double cg = (rx * ch + ry * sh) * inv, sg = fabs(rx * sh - ry * ch) * inv;     // cos, sin of the gap
-    double r = 0.0;
+// Range [lo, hi] of the displacement of `steps` further control steps along a FIXED direction that makes the angle
+// gamma, given by (cg, sg) = (cos gamma, |sin gamma|), with the node's present heading.  Step i moves by s_i in
+// [s_min, s_max] along a heading that has turned by at most i dphi_max, so its projection is s_i cos(angle_i) with
+// max(0, gamma - i dphi_max) <= angle_i <= min(pi, gamma + i dphi_max).
+//  * along the bearing to the target, hi is the closest approach: the distance of a leaf is at least its projection
+//    on that bearing, d >= D - hi.  A robot that faces away from its target, or cannot stop, is thereby known to
+//    move AWAY from it;
+//  * along the gradient of the signed line distance, wl [lo, hi] brackets the line offset q of every leaf.
+// Grids with negative speeds fall back to the isotropic range +-steps max|s|.
+__device__ __forceinline__ void projection_range(const LaunchArgs &a, double cg, double sg, int steps, double &lo,
+                                                 double &hi) {
+    if (a.g.smin < 0.0 || !(cg * cg + sg * sg < 2.0)) { hi = steps * a.g.smax; lo = -hi; return; }   // (NaN: isotropic)
+    lo = 0.0; hi = 0.0;
     for (int i = 0; i < steps; ++i) {
-        const double cm = cg >= a.cosk[i] ? 1.0 : cg * a.cosk[i] + sg * a.sink[i];       // cos(max(0, gap - (i+1) dphi_max))
-        r += cm >= 0.0 ? a.g.smax * cm : a.g.smin * cm;
+        const double ci = a.cosk[i], si = a.sink[i];                         // cos, sin of (i+1) dphi_max; -2, 0: whole circle
+        const double cmax = cg >= ci ? 1.0 : cg * ci + sg * si;              // cos(max(0, gamma - (i+1) dphi_max))
+        const double cmin = -cg >= ci ? -1.0 : cg * ci - sg * si;            // cos(min(pi, gamma + (i+1) dphi_max))
+        hi += cmax >= 0.0 ? a.g.smax * cmax : a.g.smin * cmax;
+        lo += cmin <= 0.0 ? a.g.smax * cmin : a.g.smin * cmin;
     }
-    return r;
 }
 
-// Lower bound of J_rel over every leaf that lies `steps` further control steps below a node at (xi, eta, psi) with
-// heading (cp, sp): the closest approach to the target that the steering limits allow (reach_towards_target) plus
-// the most favourable line and heading offsets (|q| <= wl steps s_max, |g| <= wh steps dphi_max).
+// min over q in [qlo, qhi] of q^2 + e q
+__device__ __forceinline__ double quad_min_range(double e, double qlo, double qhi) {
+    const double q = fmin(fmax(-0.5 * e, qlo), qhi);
+    return q * (q + e);
+}
+
+// Lower bound of J_rel over every leaf `steps` control steps below a node, from its quantities in ANY frame in which
+// (ch, sh) is its heading: (rx, ry) target relative to the node and D its length, (nx, ny) gradient of the scaled line
+// distance (length wl), ep scaled line distance, hp scaled heading error -- the closest approach the steering limits
+// allow, the most favourable line offset inside the bracket they allow, the most favourable heading offset.
+__device__ __forceinline__ double lower_bound_from(const LaunchArgs &a, const SolveParams &P, double rx, double ry,
+                                                   double D, double nx, double ny, double ch, double sh, double ep,
+                                                   double hp, double base0, int steps) {
+    double lo, reach, qlo, qhi;
+    if (D > 0.0) {
+        const double inv = 1.0 / D;
+        projection_range(a, (rx * ch + ry * sh) * inv, fabs(rx * sh - ry * ch) * inv, steps, lo, reach);
+    } else {
+        reach = steps * a.g.smax;
+    }
+    const double invl = 1.0 / P.wl;
+    projection_range(a, (nx * ch + ny * sh) * invl, fabs(nx * sh - ny * ch) * invl, steps, qlo, qhi);
+    return base0 - kWd * reach + quad_min_range(2.0 * ep, P.wl * qlo, P.wl * qhi) +
+           quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
+}
+
+// ... for a node at (xi, eta, psi) with heading (cp, sp) in the start frame
 __device__ __forceinline__ double subtree_lower_bound(const LaunchArgs &a, const SolveParams &P, double xi, double eta,
                                                       double psi, double cp, double sp, int steps) {
     const double relx = P.u0 - xi, rely = P.w0 - eta;
@@ -220,8 +246,7 @@ __device__ __forceinline__ double subtree_lower_bound(const LaunchArgs &a, const
     const double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
     const double hp = P.hp0 - P.wh * psi;
     const double base0 = kWd * (D - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
-    return base0 - kWd * reach_towards_target(a, relx, rely, D, cp, sp, steps) +
-           quad_min(2.0 * ep, P.wl * steps * a.g.smax) + quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
+    return lower_bound_from(a, P, relx, rely, D, P.nx0, P.ny0, cp, sp, ep, hp, base0, steps);
 }
 
 __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
@@ -250,17 +275,16 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     near = !(Dp >= 4.0 * a.g.smax);
     // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
     const double base0 = kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
-    // no child can do better than: one step as straight at the target as the steering allows (reach_towards_target)
-    // plus the most favourable line and heading offsets  (|q| <= wl s_max, |g| <= wh dphi_max)
+    // no child can do better than: one step as straight at the target as the steering allows, the most favourable
+    // line offset that step can produce and the most favourable heading offset (lower_bound_from)
     if (base_direct) {
         pr.eh = 0.5f * pr.e2; pr.nhh = -0.5f * pr.h2;
         pr.u2s = (float)(-2.0 * kWd * kWd * u); pr.w2s = (float)(-2.0 * kWd * kWd * w);
         pr.D2s = (float)(kWd * kWd * (Dp * Dp));
         *base_direct = base0 - kWd * Dp - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
     }
-    if (lower_bound)   // in the node's own frame the heading is (1, 0) and the target (u, w)
-        *lower_bound = base0 - kWd * reach_towards_target(a, u, w, Dp, 1.0, 0.0, 1) + quad_min(2.0 * ep, P.wl * a.g.smax) +
-                       quad_min(-2.0 * hp, P.wh * a.g.dphimax);
+    if (lower_bound)   // in the node's own frame the heading is (1, 0), the target (u, w), the line gradient (nu, nw)
+        *lower_bound = lower_bound_from(a, P, u, w, Dp, nu, nw, 1.0, 0.0, ep, hp, base0, 1);
     return base0 + (near ? dp_rem : 0.0);
 }
 

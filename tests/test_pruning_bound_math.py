@@ -1,10 +1,10 @@
 """The inequality behind the exact branch-and-bound, checked numerically on the CPU.
 
-The CUDA code (`reach_towards_target`, `subtree_lower_bound` in csrc/mpcb_kernels.cu) cuts a node when a lower bound on
+The CUDA code (`projection_range`, `lower_bound_from`, `subtree_lower_bound` in csrc/mpcb_kernels.cu) cuts a node when a lower bound on
 the cost of every leaf `k` control steps below it exceeds the best cost known.  This file restates that bound in numpy
 and checks, for EVERY node of small trees, that it never exceeds the true minimum over the node's leaves (float64
 oracle) -- i.e. that cutting by it cannot lose the argmin -- and that it is much tighter than the isotropic bound
-`d >= D - k s_max` it replaced.  The GPU-side proof is tests/test_gpu_parity.py::test_branch_and_bound_is_exact."""
+(`d >= D - k s_max`, `|q| <= wl k s_max`) it replaced.  The GPU-side proof is tests/test_gpu_parity.py::test_branch_and_bound_is_exact."""
 import math
 
 import numpy as np
@@ -41,20 +41,37 @@ def _bounds(V, B, H, x, k, cost):
     e = wl * (A * X - Bc * Y + Cc) / math.hypot(A, Bc)
     hp = wh * (C.heading_reference(tg[0], tg[1]) - P)
     reach_iso = k * smax
+    Q = wl * k * smax
     if smin < 0:
         reach = np.full_like(D, reach_iso)
+        q_lo, q_hi = np.full_like(D, -Q), np.full_like(D, Q)
     else:
-        cg = (relx * np.cos(P) + rely * np.sin(P)) / D
-        sg = np.abs(relx * np.sin(P) - rely * np.cos(P)) / D
-        reach = np.zeros_like(D)
-        for i in range(1, k + 1):
-            a = i * dmax
-            cm = np.ones_like(D) if a >= math.pi else np.where(cg >= math.cos(a), 1.0, cg * math.cos(a) + sg * math.sin(a))
-            reach += np.where(cm >= 0, smax * cm, smin * cm)
+        def proj_range(cg, sg):
+            """[lo, hi] of sum_i s_i cos(angle_i) for a direction at (cos, |sin|) = (cg, sg) from the present heading"""
+            lo, hi = np.zeros_like(D), np.zeros_like(D)
+            for i in range(1, k + 1):
+                a = i * dmax
+                if a >= math.pi:
+                    cmax, cmin = np.ones_like(D), -np.ones_like(D)
+                else:
+                    ci, si = math.cos(a), math.sin(a)
+                    cmax = np.where(cg >= ci, 1.0, cg * ci + sg * si)
+                    cmin = np.where(-cg >= ci, -1.0, cg * ci - sg * si)
+                hi += np.where(cmax >= 0, smax * cmax, smin * cmax)
+                lo += np.where(cmin <= 0, smax * cmin, smin * cmin)
+            return lo, hi
+        _, reach = proj_range((relx * np.cos(P) + rely * np.sin(P)) / D, np.abs(relx * np.sin(P) - rely * np.cos(P)) / D)
+        # scaled line offset q = wl * sum_i s_i (n . h_i), n = gradient direction of the signed line distance
+        nx, ny = A / math.hypot(A, Bc), -Bc / math.hypot(A, Bc)
+        lo, hi = proj_range(nx * np.cos(P) + ny * np.sin(P), np.abs(nx * np.sin(P) - ny * np.cos(P)))
+        q_lo, q_hi = wl * lo, wl * hi
     base = 1e4 * D + e * e + hp * hp
-    rest = _quad_min(2 * e, wl * k * smax) + _quad_min(-2 * hp, wh * k * dmax)
+    heading = _quad_min(-2 * hp, wh * k * dmax)
+    qv = np.minimum(np.maximum(-e, q_lo), q_hi)                      # vertex of q^2 + 2 e q clamped into [q_lo, q_hi]
+    rest = qv * (qv + 2 * e) + heading
+    rest_iso = _quad_min(2 * e, Q) + heading
     true_min = J.reshape(len(D), -1).min(axis=1)
-    return base - 1e4 * reach_iso + rest, base - 1e4 * reach + rest, true_min, J.min()
+    return base - 1e4 * reach_iso + rest_iso, base - 1e4 * reach + rest, true_min, J.min()
 
 
 GRIDS = {
@@ -94,3 +111,15 @@ def test_heading_aware_bound_is_what_makes_the_cut_bite():
         surv_new.append(np.mean(new <= jstar + 0.02))
     assert np.mean(surv_iso) > 0.8
     assert np.mean(surv_new) < 0.05
+
+
+def test_line_offset_interval_matters_for_the_tree_cost():
+    """With the tree script's cost (line weight 1e4) the line term dominates the differences between leaves; bounding
+    the line offset by the interval the heading range allows, instead of +-wl k s_max, is what cuts there."""
+    V, B = GRIDS["window"]
+    surv_iso, surv_new = [], []
+    for x in C.random_scenarios(12, 3):
+        iso, new, _, jstar = _bounds(V, B, 3, x, 1, C.COST_TREE)
+        surv_iso.append(np.mean(iso <= jstar + 0.02))
+        surv_new.append(np.mean(new <= jstar + 0.02))
+    assert np.mean(surv_new) < 0.25 * np.mean(surv_iso), (np.mean(surv_iso), np.mean(surv_new))
