@@ -60,3 +60,14 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", txt, re.M), f
+
+
+def test_every_option_the_library_accepts_is_documented_in_the_header():
+    api = open(os.path.join(ROOT, "diplomjourney_b200", "csrc", "mpcb_api.cu")).read()
+    body = api[api.index("int mpcb_set_option("):]
+    body = body[:body.index("\n}\n")]
+    accepted = set(re.findall(r'strcmp\(name, "(\w+)"\)', body))
+    assert {"prune", "subtree_cut", "algo", "refine"} <= accepted
+    header = open(os.path.join(ROOT, "include", "mpcb200.h")).read()
+    for name in accepted:
+        assert f'"{name}"' in header, f"option {name} is not described in include/mpcb200.h"
