@@ -25,6 +25,8 @@
 // node (projection_range, lower_bound_from, subtree_lower_bound) against a running upper bound cut nodes in pass 1, 256-node
 // tiles before pass 1 (tilecut_kernel) or whole subtrees from the root down (frontier_expand_kernel); the
 // records returned are bit-identical to evaluating every leaf.
+#include <type_traits>
+
 #include "mpcb_types.cuh"
 
 #ifndef MPCB_UNROLL2
@@ -959,21 +961,24 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
 // SMEM: ctl points into shared memory (FULL trees whose {dphi, s} table fits).
 // HT > 0: horizon known at compile time (the walk is fully unrolled, divisors live in uniform registers);
 // HT = 0: run-time horizon a.H.
-// fp32 leaf part of the leaf at (xi, eta, psi): the form pass 2 filters with, or (DIRECT) the one pass 1 ranks with
-template <bool HEAD, bool DIRECT>
+// fp32 leaf part of the leaf at (xi, eta, psi): the form pass 2 filters with, or (DIRECT) the one pass 1 ranks with.
+// ORIGIN: 1 = the solve starts on the line origin (the reference's special case applies to leaves that have not
+// moved), 0 = it does not, -1 = decide from P.flags per leaf.
+template <bool HEAD, bool DIRECT, int ORIGIN = -1>
 __device__ __forceinline__ float leafwalk_score(const SolveParams &P, const ParentRegs &pr, float xi, float eta,
                                                 float psi, float Lsp) {
+    const bool origin = ORIGIN < 0 ? (P.flags & kFlagStartIsOrigin) != 0 : ORIGIN != 0;
     const float g = 3.16227766016837952f * psi;
     if (DIRECT) {
         float L = leaf_walk_direct<HEAD>(xi, eta, psi, pr);
-        if ((P.flags & kFlagStartIsOrigin) && xi == 0.f && eta == 0.f)       // the leaf has not moved off the line origin
+        if (origin && xi == 0.f && eta == 0.f)                               // the leaf has not moved off the line origin
             L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
         return L;
     }
     const float r = __fmaf_rn(xi, xi, eta * eta);
     float L = (P.flags & kFlagNear) ? leaf_val<HEAD, true>(xi, eta, r, g, pr)
                                     : leaf_val<HEAD, false>(xi, eta, r, g, pr);
-    if ((P.flags & kFlagStartIsOrigin) && r == 0.f)
+    if (origin && r == 0.f)
         L = Lsp + (HEAD ? g * (g - pr.h2) : 0.f);
     return L;
 }
@@ -1006,20 +1011,25 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
 
 // FULL tree, indices < 2^32, horizon HT known: the control digits of the thread's leaf are kept in registers and
 // advanced by kThreads (mixed-radix add with carries) instead of being re-derived by divisions for every leaf.
-template <bool HEAD, bool SMEM, int HT>
+template <bool HEAD, bool SMEM, int HT, bool ORIGIN>
 __device__ __forceinline__ float leafwalk_eval_digits(const SolveParams &P, const ParentRegs &pr,
-                                                      const float2 *__restrict__ ctl, const unsigned (&c)[HT], float Lsp) {
+                                                      const float2 *__restrict__ ctl, unsigned ctl_shared,
+                                                      const unsigned (&c)[HT], float Lsp) {
     float xi = 0.f, eta = 0.f, psi = 0.f;
 #pragma unroll
     for (int k = 0; k < HT; ++k) {
-        float2 t = SMEM ? ctl[c[k]] : __ldg(ctl + c[k]);
+        float2 t;
+        if (SMEM)   // LDS.64 with a 32-bit shared-window address (a generic pointer costs an LD.E and 64-bit address math)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(ctl_shared + c[k] * 8u));
+        else
+            t = __ldg(ctl + c[k]);
         psi += t.x;
         float sn, cs;
         __sincosf(psi, &sn, &cs);
         xi = __fmaf_rn(t.y, cs, xi);
         eta = __fmaf_rn(t.y, sn, eta);
     }
-    return leafwalk_score<HEAD, true>(P, pr, xi, eta, psi, Lsp);      // pass 1 only: direct form
+    return leafwalk_score<HEAD, true, ORIGIN ? 1 : 0>(P, pr, xi, eta, psi, Lsp);      // pass 1 only: direct form
 }
 
 // the work loop of one CTA; HT as above
@@ -1058,21 +1068,47 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
                 for (int d = 0; d < HT; ++d) { c[d] = a.fd32[d].div(rem32); rem32 -= c[d] * a.fd32[d].d; }
                 const unsigned S = (unsigned)a.g.S, jend = (unsigned)a.u_end;
                 unsigned j32 = (unsigned)j0;
-#pragma unroll 4
-                for (int k = 0; k < kLeafPerThread; ++k) {
-                    if (j32 >= jend) break;
-                    const float L = smem ? leafwalk_eval_digits<HEAD, true, HT>(P, pr, ctl, c, Lsp)
-                                         : leafwalk_eval_digits<HEAD, false, HT>(P, pr, ctl, c, Lsp);
-                    best = fminf(best, L);
-                    j32 += kThreads;
-                    unsigned carry = 0;
+                const unsigned ctl_shared = smem ? (unsigned)__cvta_generic_to_shared(ctl) : 0u;
+                bool step_low_only = true;                     // uniform: kThreads in base S has one digit
 #pragma unroll
-                    for (int d = HT - 1; d >= 0; --d) {
-                        unsigned v = c[d] + a.step_digits[d] + carry;
-                        carry = v >= S ? 1u : 0u;
-                        c[d] = v - (carry ? S : 0u);
+                for (int d = 0; d < HT - 1; ++d) step_low_only = step_low_only && a.step_digits[d] == 0;
+                // the table's address space, the line-origin special case and the shape of the index step are uniform per
+                // launch or solve: eight loops
+                auto walk = [&](auto SM, auto ORG, auto LOW) {
+#pragma unroll 4
+                    for (int k = 0; k < kLeafPerThread; ++k) {
+                        if (j32 >= jend) break;
+                        best = fminf(best, leafwalk_eval_digits<HEAD, decltype(SM)::value, HT, decltype(ORG)::value>(
+                                               P, pr, ctl, ctl_shared, c, Lsp));
+                        j32 += kThreads;
+                        if (decltype(LOW)::value) {
+                            // kThreads < S: only the last digit steps; the carry ripples further once in S leaves
+                            unsigned v = c[HT - 1] + a.step_digits[HT - 1];
+                            if (v >= S) {
+                                v -= S;
+#pragma unroll
+                                for (int d = HT - 2; d >= 0; --d) {
+                                    if (++c[d] < S) break;
+                                    c[d] = 0;
+                                }
+                            }
+                            c[HT - 1] = v;
+                        } else {
+                            unsigned carry = 0;
+#pragma unroll
+                            for (int d = HT - 1; d >= 0; --d) {
+                                unsigned v = c[d] + a.step_digits[d] + carry;
+                                carry = v >= S ? 1u : 0u;
+                                c[d] = v - (carry ? S : 0u);
+                            }
+                        }
                     }
-                }
+                };
+                using T = std::true_type; using F = std::false_type;
+                const bool org = (P.flags & kFlagStartIsOrigin) != 0;
+                auto pick = [&](auto SM, auto ORG) { if (step_low_only) walk(SM, ORG, T{}); else walk(SM, ORG, F{}); };
+                if (smem) { if (org) pick(T{}, T{}); else pick(T{}, F{}); }
+                else      { if (org) pick(F{}, T{}); else pick(F{}, F{}); }
             } else {
                 // kLeafPerThread leaves per thread, strided by the CTA width (coalesced table reads)
 #pragma unroll 4
