@@ -395,7 +395,7 @@ def run_gpu(args):
                 bound="mufu", unit="Tops/s",
                 achieved=per_gpu_rate * mufu_a / 1e12, peak=mufu_peak / 1e12,
                 frac=per_gpu_rate * mufu_a / mufu_peak,
-                traffic=6802688,   # dram__bytes_read+write per launch, ncu --set full (profiles/r1h_cfg2_full.txt)
+                traffic=6840064,   # dram__bytes_read+write per launch, ncu --set full (profiles/r1l_cfg2_full.txt)
                 accounting="A: (2H+1) MUFU per rollout, one-thread-per-leaf design (SURVEY 8d); the prefix kernel "
                            "shares prefixes and executes 1 MUFU + 8.5 FP32 lane-ops per rollout (SASS of "
                            "prefix_min_loop_far2x2: per leaf pair and node 7 FFMA2 + 1 FADD2 at 2 issue cycles each, "
