@@ -5,6 +5,7 @@
 // on the handle's stream; the "_host" entry points add the H2D/D2H copies and a sync.
 #include "../../include/mpcb200.h"
 #include "mpcb_types.cuh"
+#include "mpcb_bounds.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -200,11 +201,7 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
         unsigned long long r = kThreads;
         for (int k = H - 1; k >= 0; --k) { a.step_digits[k] = mode == MPCB_MODE_FULL ? (unsigned)(r % S) : 0u; r = mode == MPCB_MODE_FULL ? r / S : 0; }
     }
-    for (int i = 0; i < kMaxH; ++i) {   // heading range after i+1 steps, for the pruning bounds
-        const double ang = (i + 1) * h->g.dphimax;
-        a.cosk[i] = ang < 3.141592653589793 ? std::cos(ang) : -2.0;
-        a.sink[i] = ang < 3.141592653589793 ? std::sin(ang) : 0.0;
-    }
+    bounds_set_heading_ranges(a, h->g.dphimax);   // heading range after i+1 steps, for the pruning bounds
     a.tile_units = pl.prefix ? kThreads : kThreads * kLeafPerThread;
     a.lw_smem = (!pl.prefix && mode == MPCB_MODE_FULL && h->g.S <= 4096) ? 1 : 0;
 }

@@ -5,7 +5,10 @@ the cost of every leaf `k` control steps below it exceeds the best cost known.  
 and checks, for EVERY node of small trees, that it never exceeds the true minimum over the node's leaves (float64
 oracle) -- i.e. that cutting by it cannot lose the argmin -- and that it is much tighter than the isotropic bound
 (`d >= D - k s_max`, `|q| <= wl k s_max`) it replaced.  The GPU-side proof is tests/test_gpu_parity.py::test_branch_and_bound_is_exact."""
+import ctypes
 import math
+import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -13,6 +16,7 @@ import pytest
 from oracle import closed_form as C
 
 L, DT = 0.5, 0.05
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _quad_min(e, Q):
@@ -21,7 +25,7 @@ def _quad_min(e, Q):
     return np.where(ae <= 2 * Q, -0.25 * e * e, Q * (Q - ae))
 
 
-def _bounds(V, B, H, x, k, cost):
+def _bounds(V, B, H, x, k, cost, want_poses=False):
     """(isotropic bound, heading-aware bound, true minimum over the leaves below) for every depth-(H-k) node."""
     vv, bb, dphi = C.control_tables(V, B, L, DT)
     S = len(vv)
@@ -71,6 +75,9 @@ def _bounds(V, B, H, x, k, cost):
     rest = qv * (qv + 2 * e) + heading
     rest_iso = _quad_min(2 * e, Q) + heading
     true_min = J.reshape(len(D), -1).min(axis=1)
+    poses = (X, Y, P)
+    if want_poses:
+        return base - 1e4 * reach + rest, true_min, poses, (smax, smin, dmax, wl, wh)
     return base - 1e4 * reach_iso + rest_iso, base - 1e4 * reach + rest, true_min, J.min()
 
 
@@ -123,3 +130,64 @@ def test_line_offset_interval_matters_for_the_tree_cost():
         surv_iso.append(np.mean(iso <= jstar + 0.02))
         surv_new.append(np.mean(new <= jstar + 0.02))
     assert np.mean(surv_new) < 0.25 * np.mean(surv_iso), (np.mean(surv_iso), np.mean(surv_new))
+
+
+# ---------------------------------------------------------------- the shipped CUDA source, compiled for the host
+@pytest.fixture(scope="module")
+def shipped_bound():
+    """diplomjourney_b200/csrc/mpcb_bounds.cuh (the file the kernels include) built with g++ behind a C entry point."""
+    src = os.path.join(ROOT, "tests", "native", "bounds_host.cpp")
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "bounds_host.so")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-I", os.path.join(ROOT, "diplomjourney_b200", "csrc"),
+                           "-I", cuda_inc, src, "-o", so])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.mpcb_test_subtree_lower_bounds.argtypes = [ctypes.c_double] * 3 + [dp, ctypes.c_longlong, dp, dp, dp, ctypes.c_int, dp]
+
+    def bound(x, cost, poses, consts, k):
+        """J lower bound (absolute cost) of every node in `poses` with k steps to go, by the library's own code."""
+        X, Y, P = poses
+        smax, smin, dmax, wl, wh = consts
+        xs, ys, p0, xt, yt = x
+        ox, oy = x[0], x[1]                                           # the line origin is the start in these scenarios
+        c0, s0 = math.cos(p0), math.sin(p0)
+        # SolveParams exactly as prep_kernel builds them (csrc/mpcb_kernels.cu)
+        A, Bc, Cc = yt - oy, xt - ox, xt * oy - yt * ox
+        norm = math.hypot(A, Bc)
+        rx, ry = xt - xs, yt - ys
+        u0, w0, d0 = c0 * rx + s0 * ry, c0 * ry - s0 * rx, math.hypot(rx, ry)
+        e0 = wl * (A * xs - Bc * ys + Cc) / norm
+        nx0, ny0 = wl * (A * c0 - Bc * s0) / norm, wl * (-A * s0 - Bc * c0) / norm
+        hp0 = wh * (C.heading_reference(xt, yt) - p0)
+        kbase = 1e4 * d0 + e0 * e0 + hp0 * hp0
+        solve = np.array([u0, w0, d0, e0, nx0, ny0, hp0, wl, wh])
+        xi = np.ascontiguousarray(c0 * (X - xs) + s0 * (Y - ys))      # node poses in the start frame
+        eta = np.ascontiguousarray(-s0 * (X - xs) + c0 * (Y - ys))
+        psi = np.ascontiguousarray(P - p0)
+        out = np.empty_like(xi)
+        p = lambda a: a.ctypes.data_as(dp)
+        lib.mpcb_test_subtree_lower_bounds(smax, smin, dmax, p(solve), len(xi), p(xi), p(eta), p(psi), k, p(out))
+        return kbase + out
+    return bound
+
+
+@pytest.mark.parametrize("grid", sorted(GRIDS))
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_shipped_bound_code_never_exceeds_the_true_minimum(shipped_bound, grid, cost):
+    """The same check on the code the kernels run: mpcb_bounds.cuh compiled for the host must (a) stay below the
+    float64 oracle's minimum over the leaves of every node, and (b) agree with the numpy restatement above."""
+    V, B = GRIDS[grid]
+    sc = C.random_scenarios(8, 23)
+    sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]
+    sc[1, 2] = math.atan2(sc[1, 4] - sc[1, 1], sc[1, 3] - sc[1, 0]) + math.pi
+    for x in sc:
+        for k in (1, 2, 3):
+            new, true_min, poses, consts = _bounds(V, B, 3, x, k, cost, want_poses=True)
+            lb = shipped_bound(x, cost, poses, consts, k)
+            ok = true_min < 1e7
+            scale = max(1.0, np.abs(true_min[ok]).max())
+            assert (true_min[ok] - lb[ok]).min() >= -1e-10 * scale, (grid, k, (true_min[ok] - lb[ok]).min())
+            np.testing.assert_allclose(lb[ok], new[ok], rtol=0, atol=1e-8 * scale)
