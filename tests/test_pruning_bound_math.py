@@ -1,10 +1,12 @@
 """The inequality behind the exact branch-and-bound, checked numerically on the CPU.
 
-The CUDA code (`projection_range`, `lower_bound_from`, `subtree_lower_bound` in csrc/mpcb_kernels.cu) cuts a node when a lower bound on
+The CUDA code (`projection_range`, `lower_bound_from`, `subtree_lower_bound` in csrc/mpcb_bounds.cuh) cuts a node when a lower bound on
 the cost of every leaf `k` control steps below it exceeds the best cost known.  This file restates that bound in numpy
 and checks, for EVERY node of small trees, that it never exceeds the true minimum over the node's leaves (float64
 oracle) -- i.e. that cutting by it cannot lose the argmin -- and that it is much tighter than the isotropic bound
-(`d >= D - k s_max`, `|q| <= wl k s_max`) it replaced.  The GPU-side proof is tests/test_gpu_parity.py::test_branch_and_bound_is_exact."""
+(`d >= D - k s_max`, `|q| <= wl k s_max`) it replaced.  The second half compiles the SHIPPED source, csrc/mpcb_bounds.cuh
+(the header the kernels include), for the host with g++ and runs the same check on it, so the proof is about the code
+that runs, not about a copy.  The GPU-side proof is tests/test_gpu_parity.py::test_branch_and_bound_is_exact."""
 import ctypes
 import math
 import os
