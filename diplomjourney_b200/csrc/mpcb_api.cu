@@ -60,26 +60,6 @@ constexpr unsigned long long kTileBatch = 1ULL << 23;   // subtree cut: tiles pe
 constexpr unsigned long long kWideReduceSegs = 1ULL << 15; // segments per solve from which the per-solve reduction runs grid-wide
 constexpr unsigned long long kFrontierCap = 1ULL << 22; // frontier descent: entries per list (two lists = the tile list's 64 MiB)
 
-void fastdiv32_init(FastDiv32 &f, unsigned long long d64) {
-    unsigned d = (unsigned)d64;
-    f.d = d;
-    if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
-    unsigned l = 0;
-    while ((l < 32) && ((1ULL << l) < d)) ++l;
-    f.m = (unsigned)((((1ULL << l) - d) << 32) / d) + 1u;
-    f.sh1 = 1; f.sh2 = l - 1;
-}
-
-void fastdiv_init(FastDiv64 &f, unsigned long long d) {
-    f.d = d;
-    if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
-    unsigned l = 0;
-    while ((l < 64) && ((1ULL << l) < d)) ++l;            // ceil(log2 d), d < 2^63
-    unsigned __int128 num = ((unsigned __int128)1 << 64) * (((unsigned __int128)1 << l) - d);
-    f.m = (unsigned long long)(num / d) + 1ULL;
-    f.sh1 = 1; f.sh2 = l - 1;
-}
-
 }  // namespace
 
 struct mpcb_handle_s {

@@ -8,12 +8,6 @@
 
 #include "mpcb_types.cuh"
 
-#ifdef __CUDACC__
-#define MPCB_HD __host__ __device__ __forceinline__
-#else
-#define MPCB_HD inline
-#endif
-
 namespace mpcb {
 
 // cos / sin of the heading range reachable in i+1 steps, (i+1) dphi_max; cos = -2 marks "the whole circle"

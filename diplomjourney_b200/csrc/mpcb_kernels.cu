@@ -29,6 +29,7 @@
 
 #include "mpcb_types.cuh"
 #include "mpcb_bounds.cuh"   // walk_step, projection_range, lower_bound_from, subtree_lower_bound (host/device)
+#include "mpcb_exact.cuh"    // exact_step, exact_terminal, exact_cost (host/device)
 
 #ifndef MPCB_UNROLL2
 #define MPCB_UNROLL2 8  // pairs per unrolled iteration of the two-node loop (4: -3.5 %, profiles/r1j_variants.txt)
@@ -214,55 +215,6 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     if (lower_bound)   // in the node's own frame the heading is (1, 0), the target (u, w), the line gradient (nu, nw)
         *lower_bound = lower_bound_from(a, P, u, w, Dp, nu, nw, 1.0, 0.0, ep, hp, base0, 1);
     return base0 + (near ? dp_rem : 0.0);
-}
-
-// ---- float64 evaluation by the reference's own formula and operation order
-// (iteration_of_predict math_model.py:110-114, control_criterion :82-86 / tree :82-87)
-__device__ __forceinline__ void exact_step(const LaunchArgs &a, const double4 *tab, const double *vt,
-                                           unsigned long long c, double &x, double &y, double &phi) {
-    const double dphi = __ldg(&tab[c].w);
-    const double v = __ldg(&vt[c]);
-    phi = __dadd_rn(phi, dphi);
-    double sn, cs;
-    sincos(phi, &sn, &cs);
-    x = __dadd_rn(x, __dmul_rn(__dmul_rn(v, cs), a.g.dt));
-    y = __dadd_rn(y, __dmul_rn(__dmul_rn(v, sn), a.g.dt));
-}
-
-__device__ __forceinline__ double exact_terminal(const LaunchArgs &a, const SolveParams &P, double x, double y,
-                                                 double phi) {
-    double dx = P.xt - x, dy = P.yt - y;
-    double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-    double dl;
-    if (x == P.ox && y == P.oy) dl = 1000.0;
-    else
-        dl = fabs(__dadd_rn(__dadd_rn(__dmul_rn(P.lineA, x), -__dmul_rn(P.lineB, y)), P.lineC)) / P.line_norm;
-    double dl2 = __dmul_rn(dl, dl);
-    if (a.cost_kind == 0) {
-        double ang = P.theta - phi;
-        return __dadd_rn(__dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10.0, __dmul_rn(ang, ang))),
-                         __dmul_rn(100.0, dl2));
-    }
-    return __dadd_rn(__dmul_rn(10000.0, d), __dmul_rn(10000.0, dl2));
-}
-
-// cost of leaf j (whole walk); optionally returns the poses after each step and the first control
-__device__ __noinline__ double exact_cost(const LaunchArgs &a, const SolveParams &P, long long j,
-                                          double *traj /* [H][3] or null */, int *first_c) {
-    const bool slow = (P.flags & kFlagSlow) != 0;
-    const double4 *tab = slow ? a.g.tab64_slow : a.g.tab64;
-    const double *vt = slow ? a.g.vtab_slow : a.g.vtab;
-    double x = P.xs, y = P.ys, phi = P.phi0;
-    unsigned long long rem = (unsigned long long)j;
-    for (int k = 0; k < a.H; ++k) {
-        unsigned long long c;
-        if (a.mode == 1) c = (unsigned long long)j;
-        else { c = a.fd[k].div(rem); rem -= c * a.fd[k].d; }
-        if (k == 0 && first_c) *first_c = (int)c;
-        exact_step(a, tab, vt, c, x, y, phi);
-        if (traj) { traj[3 * k] = x; traj[3 * k + 1] = y; traj[3 * k + 2] = phi; }
-    }
-    return exact_terminal(a, P, x, y, phi);
 }
 
 // pose of depth-(H-1) node p (FULL): the shared prefix of all its children, walked once per thread

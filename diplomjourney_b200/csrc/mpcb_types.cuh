@@ -25,29 +25,62 @@ constexpr int kLeafChunk = 1024;   // float4 entries of the per-control leaf tab
 // cost weights (math_model.py:86 / math_model_tree.py:87)
 constexpr double kWd = 10000.0;
 
-// Division of a 64-bit index by an invariant divisor (Granlund-Montgomery round-up form).
+#ifdef __CUDACC__
+#define MPCB_HD __host__ __device__ __forceinline__
+#define MPCB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define MPCB_HD inline
+#define MPCB_HD_NOINLINE inline
+#endif
+
+// Division of a 64-bit index by an invariant divisor (Granlund-Montgomery round-up form).  Host/device: the CPU
+// test-suite checks the very same code (tests/test_shipped_code_on_host.py).
 struct FastDiv64 {
     unsigned long long m;   // magic
     unsigned long long d;   // divisor
     unsigned sh1, sh2;
-#ifdef __CUDACC__
-    __device__ __forceinline__ unsigned long long div(unsigned long long n) const {
+    MPCB_HD unsigned long long div(unsigned long long n) const {
+#ifdef __CUDA_ARCH__
         unsigned long long t = __umul64hi(m, n);
+#else
+        unsigned long long t = (unsigned long long)(((unsigned __int128)m * n) >> 64);
+#endif
         return (t + ((n - t) >> sh1)) >> sh2;
     }
-#endif
 };
 
 // 32-bit flavour (indices below 2^32): 5 instructions per quotient instead of ~15
 struct FastDiv32 {
     unsigned m, d, sh1, sh2;
-#ifdef __CUDACC__
-    __device__ __forceinline__ unsigned div(unsigned n) const {
+    MPCB_HD unsigned div(unsigned n) const {
+#ifdef __CUDA_ARCH__
         unsigned t = __umulhi(m, n);
+#else
+        unsigned t = (unsigned)(((unsigned long long)m * n) >> 32);
+#endif
         return (t + ((n - t) >> sh1)) >> sh2;
     }
-#endif
 };
+
+inline void fastdiv32_init(FastDiv32 &f, unsigned long long d64) {
+    unsigned d = (unsigned)d64;
+    f.d = d;
+    if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
+    unsigned l = 0;
+    while ((l < 32) && ((1ULL << l) < d)) ++l;
+    f.m = (unsigned)((((1ULL << l) - d) << 32) / d) + 1u;
+    f.sh1 = 1; f.sh2 = l - 1;
+}
+
+inline void fastdiv_init(FastDiv64 &f, unsigned long long d) {
+    f.d = d;
+    if (d <= 1) { f.m = 0; f.sh1 = 0; f.sh2 = 0; return; }
+    unsigned l = 0;
+    while ((l < 64) && ((1ULL << l) < d)) ++l;            // ceil(log2 d), d < 2^63
+    unsigned __int128 num = ((unsigned __int128)1 << 64) * (((unsigned __int128)1 << l) - d);
+    f.m = (unsigned long long)(num / d) + 1ULL;
+    f.sh1 = 1; f.sh2 = l - 1;
+}
 
 constexpr int kLeafPerThread = 8;  // leafwalk: leaves per thread per tile (tile = kThreads * kLeafPerThread leaves)
 

@@ -1,0 +1,56 @@
+// TEST HARNESS (not part of the product): compiles SHIPPED pieces of the CUDA library for the host with g++ --
+// csrc/mpcb_exact.cuh (the float64 leaf evaluation whose results the library returns) and the invariant-divisor
+// index decoding of csrc/mpcb_types.cuh -- so that tests/test_shipped_code_on_host.py can check them against the
+// reference's golden outputs and the oracle without a GPU.
+#include <cmath>
+#include <vector>
+
+#include "mpcb_exact.cuh"
+
+extern "C" void mpcb_test_fastdiv64(unsigned long long d, long long count, const unsigned long long *n,
+                                    unsigned long long *q) {
+    mpcb::FastDiv64 f;
+    mpcb::fastdiv_init(f, d);
+    for (long long i = 0; i < count; ++i) q[i] = f.div(n[i]);
+}
+
+extern "C" void mpcb_test_fastdiv32(unsigned d, long long count, const unsigned *n, unsigned *q) {
+    mpcb::FastDiv32 f;
+    mpcb::fastdiv32_init(f, d);
+    for (long long i = 0; i < count; ++i) q[i] = f.div(n[i]);
+}
+
+// cost of leaf j of one solve (mode 0 FULL / 1 HELD), poses after each step and the first control, computed by
+// mpcb::exact_cost from tables built as mpcb_set_grid builds them and solve parameters as prep_kernel builds them
+extern "C" double mpcb_test_exact_cost(const double *v, int nv, const double *beta, int nb, double L, double delta_t,
+                                       int mode, int cost_kind, int H, const double *state, const double *target,
+                                       const double *origin, long long j, double *traj, int *first_c) {
+    const int S = nv * nb;
+    std::vector<double4> tab(S);
+    std::vector<double> vt(S);
+    for (int iv = 0; iv < nv; ++iv)
+        for (int ib = 0; ib < nb; ++ib) {
+            const int c = iv * nb + ib;
+            const double dphi = (v[iv] / L) * std::tan(beta[ib]) * delta_t;   // math_model.py:77-78 x delta_t
+            tab[c] = make_double4(std::cos(dphi), std::sin(dphi), v[iv] * delta_t, dphi);
+            vt[c] = v[iv];
+        }
+    mpcb::LaunchArgs a = {};
+    a.g.tab64 = tab.data(); a.g.vtab = vt.data(); a.g.tab64_slow = tab.data(); a.g.vtab_slow = vt.data();
+    a.g.S = S; a.g.nb = nb; a.g.dt = delta_t;
+    a.mode = mode; a.H = H; a.cost_kind = cost_kind;
+    unsigned long long pw = 1;
+    for (int k = H - 1; k >= 0; --k) {   // fd[k].d = S^(H-1-k), as fill_args (mpcb_api.cu)
+        mpcb::fastdiv_init(a.fd[k], pw);
+        if (mode == 0) pw *= (unsigned long long)S;
+    }
+    mpcb::SolveParams P = {};
+    P.xs = state[0]; P.ys = state[1]; P.phi0 = state[2];
+    P.xt = target[0]; P.yt = target[1];
+    P.ox = origin[0]; P.oy = origin[1];
+    P.theta = std::atan(P.xt / P.yt);
+    P.lineA = P.yt - P.oy; P.lineB = P.xt - P.ox;
+    P.lineC = P.xt * P.oy - P.yt * P.ox;
+    P.line_norm = std::sqrt(P.lineA * P.lineA + P.lineB * P.lineB);
+    return mpcb::exact_cost(a, P, j, traj, first_c);
+}
