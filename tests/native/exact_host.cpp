@@ -24,19 +24,26 @@ extern "C" void mpcb_test_fastdiv32(unsigned d, long long count, const unsigned 
 // mpcb::exact_cost from tables built as mpcb_set_grid builds them and solve parameters as prep_kernel builds them
 extern "C" double mpcb_test_exact_cost(const double *v, int nv, const double *beta, int nb, double L, double delta_t,
                                        int mode, int cost_kind, int H, const double *state, const double *target,
-                                       const double *origin, long long j, double *traj, int *first_c) {
+                                       const double *origin, long long j, double *traj, int *first_c, int slow,
+                                       double v_min) {
     const int S = nv * nb;
-    std::vector<double4> tab(S);
-    std::vector<double> vt(S);
+    std::vector<double4> tab(S), tab_slow(S);
+    std::vector<double> vt(S), vt_slow(S);
+    double vmin_grid = v[0];
+    for (int i = 1; i < nv; ++i) vmin_grid = std::fmin(vmin_grid, v[i]);
+    const double v_slow = vmin_grid > v_min ? vmin_grid : v_min;             // math_model_tree.py:312-316
     for (int iv = 0; iv < nv; ++iv)
         for (int ib = 0; ib < nb; ++ib) {
             const int c = iv * nb + ib;
-            const double dphi = (v[iv] / L) * std::tan(beta[ib]) * delta_t;   // math_model.py:77-78 x delta_t
-            tab[c] = make_double4(std::cos(dphi), std::sin(dphi), v[iv] * delta_t, dphi);
-            vt[c] = v[iv];
+            for (int variant = 0; variant < 2; ++variant) {
+                const double vc = variant ? v_slow : v[iv];
+                const double dphi = (vc / L) * std::tan(beta[ib]) * delta_t;   // math_model.py:77-78 x delta_t
+                (variant ? tab_slow : tab)[c] = make_double4(std::cos(dphi), std::sin(dphi), vc * delta_t, dphi);
+                (variant ? vt_slow : vt)[c] = vc;
+            }
         }
     mpcb::LaunchArgs a = {};
-    a.g.tab64 = tab.data(); a.g.vtab = vt.data(); a.g.tab64_slow = tab.data(); a.g.vtab_slow = vt.data();
+    a.g.tab64 = tab.data(); a.g.vtab = vt.data(); a.g.tab64_slow = tab_slow.data(); a.g.vtab_slow = vt_slow.data();
     a.g.S = S; a.g.nb = nb; a.g.dt = delta_t;
     a.mode = mode; a.H = H; a.cost_kind = cost_kind;
     unsigned long long pw = 1;
@@ -52,5 +59,6 @@ extern "C" double mpcb_test_exact_cost(const double *v, int nv, const double *be
     P.lineA = P.yt - P.oy; P.lineB = P.xt - P.ox;
     P.lineC = P.xt * P.oy - P.yt * P.ox;
     P.line_norm = std::sqrt(P.lineA * P.lineA + P.lineB * P.lineB);
+    P.flags = slow ? mpcb::kFlagSlow : 0;
     return mpcb::exact_cost(a, P, j, traj, first_c);
 }

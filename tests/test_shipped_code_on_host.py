@@ -34,12 +34,12 @@ def host():
     lib.mpcb_test_fastdiv32.argtypes = [ctypes.c_uint32, ctypes.c_longlong, u32p, u32p]
     lib.mpcb_test_exact_cost.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_longlong, dp,
-                                         ctypes.POINTER(ctypes.c_int)]
+                                         ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_double]
     lib.mpcb_test_exact_cost.restype = ctypes.c_double
     return lib
 
 
-def _exact(lib, V, B, mode, cost, H, state, target, origin, j):
+def _exact(lib, V, B, mode, cost, H, state, target, origin, j, slow=False):
     v = np.ascontiguousarray(V, np.float64); b = np.ascontiguousarray(B, np.float64)
     st = np.ascontiguousarray(np.asarray(state, np.float64)[:3]); tg = np.ascontiguousarray(target, np.float64)
     og = np.ascontiguousarray(origin, np.float64)
@@ -47,7 +47,7 @@ def _exact(lib, V, B, mode, cost, H, state, target, origin, j):
     dp = ctypes.POINTER(ctypes.c_double)
     p = lambda a: a.ctypes.data_as(dp)
     J = lib.mpcb_test_exact_cost(p(v), v.size, p(b), b.size, L, DT, mode, 0 if cost == C.COST_MM else 1, H,
-                                 p(st), p(tg), p(og), int(j), p(traj), ctypes.byref(fc))
+                                 p(st), p(tg), p(og), int(j), p(traj), ctypes.byref(fc), 1 if slow else 0, C.CONFIG["v_min"])
     return J, traj, fc.value
 
 
@@ -100,20 +100,22 @@ def test_exact_evaluation_reproduces_the_reference_full_ticks(host, golden):
 
 
 def test_exact_evaluation_reproduces_the_reference_held_solves(host, golden):
-    """The online controller's solves (HELD tree, tree-script cost) without the slow-down override."""
+    """The online controller's solves (HELD tree, tree-script cost), with and without the slow-down override
+    (every velocity := max(min(V), v_min), math_model_tree.py:312-316)."""
     g = golden("held_single")
-    checked = 0
+    checked = slowed = 0
     for case in g["cases"]:
-        if case["slow"]:
-            continue
-        o = C.solve_held(case["state"], case["target"], case["origin"], case["vector_v"], case["vector_beta"], 3, C.COST_TREE)
+        slow = bool(case["slow"])
+        slowed += slow
+        o = C.solve_held(case["state"], case["target"], case["origin"], case["vector_v"], case["vector_beta"], 3, C.COST_TREE,
+                         slow=slow)
         J, traj, fc = _exact(host, case["vector_v"], case["vector_beta"], 1, C.COST_TREE, 3, case["state"], case["target"],
-                             case["origin"], o["index"])
+                             case["origin"], o["index"], slow=slow)
         assert J == pytest.approx(o["cost"], rel=1e-12)
         np.testing.assert_allclose(traj, np.array(case["traj"]), rtol=0, atol=1e-12)
         assert fc == o["index"]
         checked += 1
-    assert checked >= 4
+    assert checked >= 8 and slowed >= 1
 
 
 @pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
