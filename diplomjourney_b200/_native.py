@@ -70,9 +70,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
-        _build.build_library()
+    path = _build.build_library()       # returns at once unless a source is newer than the library (or MPCB_LIB is set)
     lib = C.CDLL(path)
     vp = C.c_void_p
     lib.mpcb_version.restype = C.c_int
@@ -95,7 +93,13 @@ def load():
     loop = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mpcb_held_closed_loop_host.argtypes = loop
     lib.mpcb_held_closed_loop_device.argtypes = loop
+    win = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mpcb_solve_held_windows_host.argtypes = win
+    lib.mpcb_solve_held_windows_device.argtypes = win
     lib.mpcb_full_closed_loop_host.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_double, C.c_int, vp, vp, vp]
+    split = [vp, vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.mpcb_solve_tree_split_host.argtypes = split
+    lib.mpcb_solve_tree_split_device.argtypes = split
     lib.mpcb_allreduce_min.argtypes = [vp, vp, vp, vp]
     lib.mpcb_nccl_unique_id.argtypes = [vp]
     lib.mpcb_nccl_comm_create.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
@@ -128,6 +132,7 @@ class Solver:
         self.device = int(device)
         self.S = 0
         self.grid = None
+        self._owner = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -152,6 +157,7 @@ class Solver:
                                         float(L), float(delta_t), float(v_min)))
         self.S = v.size * b.size
         self.grid = (v, b, float(L), float(delta_t), float(v_min))
+        self._owner = None      # whoever cached "my grid is set on this solver" must set it again
 
     def set_option(self, name: str, value: float):
         self._ck(self.lib.mpcb_set_option(self.h, name.encode(), float(value)))
@@ -202,6 +208,51 @@ class Solver:
         self._ck(self.lib.mpcb_solve_batch_device(self.h, mode, cost, H, int(N), vp(state), vp(target), vp(origin),
                                                   vp(threshold), vp(flags), lo, hi, vp(out_cost), vp(out_index),
                                                   vp(out_traj), vp(out_ctl)))
+
+    def solve_tree_split(self, comm: "NcclComm", cost, H, state, target, origin, threshold=None):
+        """ONE FULL tree per solve shared by the ranks of ``comm`` (mpcb_solve_tree_split_host): collective call,
+        every rank passes the same arguments and gets the whole tree's result (global leaf indices)."""
+        st = _arr(state, np.float64)
+        st = st.reshape(-1, st.shape[-1])[:, :3].copy() if st.ndim > 1 else st[:3].reshape(1, 3).copy()
+        N = st.shape[0]
+        tg = _arr(np.broadcast_to(_arr(target, np.float64, (-1, 2)), (N, 2)), np.float64)
+        og = _arr(np.broadcast_to(_arr(origin, np.float64, (-1, 2)), (N, 2)), np.float64)
+        thr = None if threshold is None else _arr(np.broadcast_to(np.asarray(threshold, np.float64), (N,)), np.float64)
+        cost_o, idx_o = np.empty(N, np.float64), np.empty(N, np.int64)
+        traj_o, ctl_o = np.empty((N, H, 3), np.float64), np.empty((N, 2), np.float64)
+        self._ck(self.lib.mpcb_solve_tree_split_host(self.h, comm.comm, cost, H, N, _ptr(st), _ptr(tg), _ptr(og),
+                                                     _ptr(thr), _ptr(cost_o), _ptr(idx_o), _ptr(traj_o), _ptr(ctl_o)))
+        return dict(cost=cost_o, index=idx_o, traj=traj_o, first_control=ctl_o)
+
+    def solve_tree_split_device(self, comm: "NcclComm", cost, H, N, state, target, origin, threshold, out_cost,
+                                out_index, out_traj, out_ctl):
+        """Device-pointer flavour (mpcb_solve_tree_split_device): enqueues the solve of this rank's share, the
+        16-byte all-gather and the finalisation on self.stream; does not synchronise."""
+        vp = lambda x: C.c_void_p(int(x)) if x else None
+        self._ck(self.lib.mpcb_solve_tree_split_device(self.h, comm.comm, cost, H, int(N), vp(state), vp(target),
+                                                       vp(origin), vp(threshold), vp(out_cost), vp(out_index),
+                                                       vp(out_traj), vp(out_ctl)))
+
+    def solve_held_windows(self, params: "LoopParams", state, v_beta, target, origin, threshold=None, flags=None):
+        """One online tick of N robots, each with its OWN acceleration window built on the device around its current
+        (v, beta) (mpcb_solve_held_windows_host).  state[N,3], v_beta[N,2], target[N,2], origin[N,2].
+        Returns dict(cost, index, traj, first_control, shape[N,2] = (nV, nB))."""
+        st = _arr(state, np.float64)
+        st = st.reshape(-1, st.shape[-1])[:, :3].copy()
+        N = st.shape[0]
+        vb = _arr(np.broadcast_to(_arr(v_beta, np.float64, (-1, 2)), (N, 2)), np.float64)
+        tg = _arr(np.broadcast_to(_arr(target, np.float64, (-1, 2)), (N, 2)), np.float64)
+        og = _arr(np.broadcast_to(_arr(origin, np.float64, (-1, 2)), (N, 2)), np.float64)
+        thr = None if threshold is None else _arr(np.broadcast_to(np.asarray(threshold, np.float64), (N,)), np.float64)
+        fl = None if flags is None else _arr(np.broadcast_to(np.asarray(flags, np.uint8), (N,)), np.uint8)
+        H = params.H
+        cost_o, idx_o = np.empty(N, np.float64), np.empty(N, np.int64)
+        traj_o, ctl_o = np.empty((N, H, 3), np.float64), np.empty((N, 2), np.float64)
+        shape_o = np.empty((N, 2), np.int32)
+        self._ck(self.lib.mpcb_solve_held_windows_host(self.h, C.byref(params), N, _ptr(st), _ptr(vb), _ptr(tg), _ptr(og),
+                                                       _ptr(thr), _ptr(fl), _ptr(cost_o), _ptr(idx_o), _ptr(traj_o),
+                                                       _ptr(ctl_o), _ptr(shape_o)))
+        return dict(cost=cost_o, index=idx_o, traj=traj_o, first_control=ctl_o, shape=shape_o)
 
     def held_closed_loop(self, params: "LoopParams", init, target, origin, first_threshold=None, slow_steps=None):
         """Whole closed loops of the online controller for a batch of robots on the device

@@ -6,6 +6,7 @@ nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the t
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -15,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MPCB_LIB") or os.path.join(HERE, "lib", "libmpcb200.so")   # MPCB_LIB: developer override
 SOURCES = ["mpcb_kernels.cu", "mpcb_loop.cu", "mpcb_api.cu", "mpcb_nccl.cu"]
-HEADERS = ["mpcb_types.cuh", "mpcb_bounds.cuh", "mpcb_exact.cuh", os.path.join("..", "..", "include", "mpcb200.h")]
+HEADERS = ["mpcb_types.cuh", "mpcb_bounds.cuh", "mpcb_exact.cuh", "mpcb_handle.cuh", os.path.join("..", "..", "include", "mpcb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared",
@@ -29,17 +30,32 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def source_hash() -> str:
+    """Hash of everything the library is built from (sources, headers, flags): what decides staleness.  mtimes do
+    not survive a copy of the tree to another box; contents do."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
+def needs_build(lib: str | None = None) -> bool:
+    lib = lib or LIB
+    try:
+        with open(lib + ".srchash") as f:
+            return not os.path.exists(lib) or f.read().strip() != source_hash()
+    except OSError:
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Compiles the library with nvcc unless the one on disk was built from these very sources (force=True: always).
+    A library named by MPCB_LIB is a developer's variant and is used as it is."""
     out = out or LIB
-    if not force and out == LIB and not needs_build():
+    if not force and out == LIB and (os.environ.get("MPCB_LIB") or not needs_build()):
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"MPCB_LIB={LIB} does not exist")
         return LIB
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
@@ -47,6 +63,9 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if not extra_flags:
+        with open(out + ".srchash", "w") as f:
+            f.write(source_hash() + "\n")
     if verbose:
         print(r.stderr)
     return out

@@ -6,6 +6,7 @@
 #include "../../include/mpcb200.h"
 #include "mpcb_types.cuh"
 #include "mpcb_bounds.cuh"
+#include "mpcb_handle.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -24,7 +25,7 @@ cudaError_t launch_reduce_compact_wide(cudaStream_t, const LaunchArgs &, double 
                                        int sms, int *launches);
 cudaError_t launch_probe(cudaStream_t, const LaunchArgs &, int sms);
 cudaError_t launch_tilecut(cudaStream_t, const LaunchArgs &, unsigned long long g_begin, unsigned long long g_end,
-                           unsigned long long *list, unsigned *count);
+                           unsigned long long *list, unsigned *count, unsigned long long list_cap);
 cudaError_t launch_frontier_expand(cudaStream_t, const LaunchArgs &, int k, const unsigned long long *src,
                                    const unsigned *src_count, unsigned long long *dst, unsigned *dst_count,
                                    unsigned *overflow, int sms);
@@ -33,63 +34,15 @@ cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *j
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
 cudaError_t launch_held_small(cudaStream_t, const SmallArgs &);
 cudaError_t launch_full_apply(cudaStream_t, const FullLoopArgs &);
+cudaError_t launch_held_windows(cudaStream_t, const WindowArgs &, int sms);
+cudaError_t launch_split_pack(cudaStream_t, const LaunchArgs &, SplitRec *mine);
+cudaError_t launch_split_pick(cudaStream_t, const LaunchArgs &, const SplitRec *all, int nranks);
+bool nccl_available();
+int nccl_comm_info(void *comm, int *nranks, int *rank);
+int nccl_allgather_bytes(void *comm, const void *send, void *recv, size_t bytes, cudaStream_t st);
 }  // namespace mpcb
 
 using namespace mpcb;
-
-namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
-};
-
-constexpr unsigned long long kSegCap = 1ULL << 22;
-constexpr unsigned long long kTileBatch = 1ULL << 23;   // subtree cut: tiles per batch (survivor list <= 64 MiB)
-constexpr unsigned long long kWideReduceSegs = 1ULL << 15; // segments per solve from which the per-solve reduction runs grid-wide
-constexpr unsigned long long kFrontierCap = 1ULL << 22; // frontier descent: entries per list (two lists = the tile list's 64 MiB)
-
-}  // namespace
-
-struct mpcb_handle_s {
-    int device = 0, sms = 148;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    // grid
-    bool have_grid = false, tables_ready = false;
-    std::vector<double> hv, hb;         // host copy of the raw grids
-    double L = 0, delta_t = 0, v_min = 0, v_slow = 0;
-    GridTables g{};
-    DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, ctl32, ctl32_slow;
-    // options
-    double tol_scale = 1.0;
-    int algo = MPCB_ALGO_AUTO;
-    int refine = 1;
-    int small_path = 1;
-    int dump_direct = 0;  // mpcb_dump_leaves_host, prefix: dump the values pass 1 ranks with
-    int npt = 2;          // exhaustive prefix pass 1: nodes per thread (2: +6 %, tools/ubench)
-    unsigned long long frontier_cap = kFrontierCap;   // entries per frontier list (option, diagnostics: a tiny value forces the fallback)
-    int subtree_cut = 2;       // pruned pass 1, H >= 3: 0 off, 1 depth-(H-2) bound per 256-node tile, 2 auto (frontier descent from the root for trees of more than one tile batch), 3 frontier always
-    int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
-    // scratch
-    DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list, reduce_scratch;
-    DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
-    DevBuf loop_log, loop_ticks, loop_status, small_in, small_out, fl_last, fl_k, fl_have, fl_flags, fl_count;
-    void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path
-    size_t pin_in_cap = 0, pin_out_cap = 0;
-    mpcb_stats stats{};
-};
 
 namespace {
 
@@ -303,7 +256,7 @@ int mpcb_destroy(mpcb_handle *h) {
                       &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
                       &h->loop_status, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
-                      &h->fl_count})
+                      &h->fl_count, &h->nccl_scratch})
         b->release();
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -330,6 +283,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
+    else if (!strcmp(name, "screen")) h->screen = value != 0.0;
     else if (!strcmp(name, "subtree_cut")) {
         if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0) return fail(h, MPCB_ERR_INVALID, "subtree_cut must be 0, 1, 2 or 3");
         h->subtree_cut = (int)value;
@@ -365,10 +319,15 @@ int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double *beta, i
     return MPCB_OK;
 }
 
-int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
-                            const double *target, const double *origin, const double *threshold,
-                            const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
-                            int64_t *best_index, double *best_traj, double *first_control) {
+}  // extern "C"
+
+// The solve behind every batch entry point.  split_comm != null: ONE tree (per solve) shared by the ranks of an NCCL
+// communicator -- this rank expands the first controls of its contiguous share, the per-rank (cost, index) records
+// are all-gathered (16 bytes per solve and rank, one collective) and every rank finalises the same winner.
+static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                      const double *target, const double *origin, const double *threshold,
+                      const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
+                      int64_t *best_index, double *best_traj, double *first_control, void *split_comm) {
     if (!h) return MPCB_ERR_INVALID;
     if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
     if (H < 1 || H > MPCB_MAX_H) return fail(h, MPCB_ERR_INVALID, "H=%d out of range [1,%d]", H, MPCB_MAX_H);
@@ -380,6 +339,15 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     CK(cudaSetDevice(h->device));
     int rc = ensure_tables(h);
     if (rc) return rc;
+    int nranks = 1, rank = 0;
+    if (split_comm) {
+        if (mode != MPCB_MODE_FULL) return fail(h, MPCB_ERR_INVALID, "only a FULL tree is split across ranks");
+        if (nccl_comm_info(split_comm, &nranks, &rank) != MPCB_OK) return fail(h, MPCB_ERR_NCCL, "bad NCCL communicator");
+        // contiguous, balanced ranges of the first control: rank order = leaf-index order
+        const long long S = h->g.S, per = S / nranks, extra = S % nranks;
+        i0_begin = rank * per + std::min<long long>(rank, extra);
+        i0_end = i0_begin + per + (rank < extra ? 1 : 0);
+    }
     Plan pl;
     rc = make_plan(h, mode, H, N, i0_begin, i0_end, MPCB_ALGO_AUTO, pl);
     if (rc) return rc;
@@ -425,11 +393,12 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     a.ub = h->ub.as<unsigned long long>();
     a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
     a.npt = h->npt;
+    a.screen = (pl.prefix && !a.prune && H >= 2 && h->npt >= 2) ? h->screen : 0;
 
     int launches = 0;
     CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, (pl.prefix ? 1 : 0) | (mode == MPCB_MODE_HELD ? 2 : 0),
                    h->g.smax, h->g.dphimax, h->tol_scale, h->sp.as<SolveParams>())); ++launches;
-    if (a.prune) {
+    if (a.prune || a.screen) {   // exact upper bound on every solve's minimum from the S held sequences
         CK(launch_probe(h->stream, a, h->sms)); ++launches;
     }
     const unsigned __int128 tiles_all = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
@@ -476,7 +445,7 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
             a.tile_count = tile_count;
             for (unsigned long long g0 = 0; g0 < all; g0 += batch) {
                 if (g0 || frontier) CK(cudaMemsetAsync(tile_count, 0, sizeof(unsigned), h->stream));
-                CK(launch_tilecut(h->stream, a, g0, std::min(all, g0 + batch), lists, tile_count)); ++launches;
+                CK(launch_tilecut(h->stream, a, g0, std::min(all, g0 + batch), lists, tile_count, batch)); ++launches;
                 CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
             }
             a.tile_list = nullptr; a.tile_count = nullptr;
@@ -494,6 +463,14 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 2, pl.prefix, h->sms)); ++launches;
     }
+    if (split_comm) {
+        CK(h->nccl_scratch.ensure(sizeof(SplitRec) * (size_t)N * (nranks + 1)));
+        SplitRec *mine = h->nccl_scratch.as<SplitRec>(), *all = mine + N;
+        CK(launch_split_pack(h->stream, a, mine)); ++launches;
+        if (nccl_allgather_bytes(split_comm, mine, all, sizeof(SplitRec) * (size_t)N, h->stream) != MPCB_OK)
+            return fail(h, MPCB_ERR_NCCL, "ncclAllGather failed");
+        CK(launch_split_pick(h->stream, a, all, nranks)); ++launches;
+    }
     CK(launch_finalize(h->stream, a, best_cost, (long long *)best_index, best_traj, first_control)); ++launches;
 
     h->stats.units = (int64_t)units;
@@ -504,6 +481,25 @@ int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int6
     h->stats.refine_segments = -1;   // resolved lazily by mpcb_get_stats
     h->stats.refine_candidates = -1;
     return MPCB_OK;
+}
+
+extern "C" {
+
+int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                            const double *target, const double *origin, const double *threshold,
+                            const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
+                            int64_t *best_index, double *best_traj, double *first_control) {
+    return solve_core(h, mode, cost_kind, H, N, state, target, origin, threshold, flags, i0_begin, i0_end, best_cost,
+                      best_index, best_traj, first_control, nullptr);
+}
+
+int mpcb_solve_tree_split_device(mpcb_handle *h, void *nccl_comm, int cost_kind, int H, int64_t N, const double *state,
+                                 const double *target, const double *origin, const double *threshold,
+                                 double *best_cost, int64_t *best_index, double *best_traj, double *first_control) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (!nccl_comm || !nccl_available()) return fail(h, MPCB_ERR_NCCL, "split tree: no NCCL communicator");
+    return solve_core(h, MPCB_MODE_FULL, cost_kind, H, N, state, target, origin, threshold, nullptr, 0, -1, best_cost,
+                      best_index, best_traj, first_control, nccl_comm);
 }
 
 int mpcb_get_stats(mpcb_handle *h, mpcb_stats *out) {
@@ -577,21 +573,11 @@ static int solve_held_small(mpcb_handle *h, int cost_kind, int H, int64_t N, con
     return MPCB_OK;
 }
 
-int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
-                          const double *target, const double *origin, const double *threshold,
-                          const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
-                          int64_t *best_index, double *best_traj, double *first_control) {
-    if (!h) return MPCB_ERR_INVALID;
-    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
-    if (!state || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
-    if (H < 1 || H > MPCB_MAX_H) return fail(h, MPCB_ERR_INVALID, "H=%d out of range [1,%d]", H, MPCB_MAX_H);
-    if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
-    if ((cost_kind != MPCB_COST_MM && cost_kind != MPCB_COST_TREE) || (mode != MPCB_MODE_FULL && mode != MPCB_MODE_HELD))
-        return fail(h, MPCB_ERR_INVALID, "bad mode/cost");
-    CK(cudaSetDevice(h->device));
-    if (mode == MPCB_MODE_HELD && h->small_path && h->g.S <= 4096 && h->hb.size() <= 4096 && N <= 8192)
-        return solve_held_small(h, cost_kind, H, N, state, target, origin, threshold, flags, best_cost, best_index,
-                                best_traj, first_control);
+// host buffers -> device staging -> solve_core -> host buffers (one synchronisation)
+static int solve_host_staged(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                             const double *target, const double *origin, const double *threshold,
+                             const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
+                             int64_t *best_index, double *best_traj, double *first_control, void *split_comm) {
     cudaStream_t st = h->stream;
     CK(h->in_state.ensure(sizeof(double) * 3 * N));
     CK(h->in_target.ensure(sizeof(double) * 2 * N));
@@ -615,10 +601,9 @@ int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_
     CK(h->out_index.ensure(sizeof(int64_t) * N));
     CK(h->out_traj.ensure(sizeof(double) * 3 * H * N));
     CK(h->out_ctl.ensure(sizeof(double) * 2 * N));
-    int rc = mpcb_solve_batch_device(h, mode, cost_kind, H, N, h->in_state.as<double>(), h->in_target.as<double>(),
-                                     h->in_origin.as<double>(), d_thr, d_flags, i0_begin, i0_end,
-                                     h->out_cost.as<double>(), h->out_index.as<int64_t>(), h->out_traj.as<double>(),
-                                     h->out_ctl.as<double>());
+    int rc = solve_core(h, mode, cost_kind, H, N, h->in_state.as<double>(), h->in_target.as<double>(),
+                        h->in_origin.as<double>(), d_thr, d_flags, i0_begin, i0_end, h->out_cost.as<double>(),
+                        h->out_index.as<int64_t>(), h->out_traj.as<double>(), h->out_ctl.as<double>(), split_comm);
     if (rc) return rc;
     if (best_cost) CK(cudaMemcpyAsync(best_cost, h->out_cost.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
     if (best_index) CK(cudaMemcpyAsync(best_index, h->out_index.p, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, st));
@@ -626,6 +611,46 @@ int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_
     if (first_control) CK(cudaMemcpyAsync(first_control, h->out_ctl.p, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return MPCB_OK;
+}
+
+static int check_host_args(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                           const double *target, const double *origin) {
+    if (!state || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
+    if (H < 1 || H > MPCB_MAX_H) return fail(h, MPCB_ERR_INVALID, "H=%d out of range [1,%d]", H, MPCB_MAX_H);
+    if (!h->have_grid) return fail(h, MPCB_ERR_NO_GRID, "mpcb_set_grid has not been called");
+    if ((cost_kind != MPCB_COST_MM && cost_kind != MPCB_COST_TREE) || (mode != MPCB_MODE_FULL && mode != MPCB_MODE_HELD))
+        return fail(h, MPCB_ERR_INVALID, "bad mode/cost");
+    (void)N;
+    return MPCB_OK;
+}
+
+int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N, const double *state,
+                          const double *target, const double *origin, const double *threshold,
+                          const uint8_t *flags, int64_t i0_begin, int64_t i0_end, double *best_cost,
+                          int64_t *best_index, double *best_traj, double *first_control) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
+    int rc = check_host_args(h, mode, cost_kind, H, N, state, target, origin);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (mode == MPCB_MODE_HELD && h->small_path && h->g.S <= 4096 && h->hb.size() <= 4096 && N <= 8192)
+        return solve_held_small(h, cost_kind, H, N, state, target, origin, threshold, flags, best_cost, best_index,
+                                best_traj, first_control);
+    return solve_host_staged(h, mode, cost_kind, H, N, state, target, origin, threshold, flags, i0_begin, i0_end,
+                             best_cost, best_index, best_traj, first_control, nullptr);
+}
+
+int mpcb_solve_tree_split_host(mpcb_handle *h, void *nccl_comm, int cost_kind, int H, int64_t N, const double *state,
+                               const double *target, const double *origin, const double *threshold,
+                               double *best_cost, int64_t *best_index, double *best_traj, double *first_control) {
+    if (!h) return MPCB_ERR_INVALID;
+    if (!nccl_comm || !nccl_available()) return fail(h, MPCB_ERR_NCCL, "split tree: no NCCL communicator");
+    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
+    int rc = check_host_args(h, MPCB_MODE_FULL, cost_kind, H, N, state, target, origin);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    return solve_host_staged(h, MPCB_MODE_FULL, cost_kind, H, N, state, target, origin, threshold, nullptr, 0, -1,
+                             best_cost, best_index, best_traj, first_control, nccl_comm);
 }
 
 int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int algo, const double *state,
@@ -738,6 +763,7 @@ int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_
         CK(cudaMemcpyAsync(h->in_flags.p, slow_steps, sizeof(int) * N, cudaMemcpyHostToDevice, st));
         d_slow = h->in_flags.as<int>();
     }
+    CK(cudaMemsetAsync(h->loop_log.p, 0xFF, sizeof(double) * nlog, st));     // NaN pattern for the rows no tick wrote
     int rc = mpcb_held_closed_loop_device(h, p, N, h->in_state.as<double>(), h->in_target.as<double>(),
                                           h->in_origin.as<double>(), d_thr, d_slow, h->loop_log.as<double>(),
                                           h->loop_ticks.as<int>(), h->loop_status.as<int>());
@@ -745,6 +771,87 @@ int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_
     CK(cudaMemcpyAsync(out_log, h->loop_log.p, sizeof(double) * nlog, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_ticks, h->loop_ticks.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_status, h->loop_status.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MPCB_OK;
+}
+
+static int check_window_params(mpcb_handle *h, const mpcb_loop_params *p) {
+    if (p->H < 1 || p->H > MPCB_MAX_H || p->n_v < 1 || p->n_beta < 1 || p->n_v > 128 || p->n_beta > 128 ||
+        (p->cost_kind != MPCB_COST_MM && p->cost_kind != MPCB_COST_TREE))
+        return fail(h, MPCB_ERR_INVALID, "window parameters out of range (H=%d, n_v=%d, n_beta=%d, cost=%d)", p->H, p->n_v,
+                    p->n_beta, p->cost_kind);
+    return MPCB_OK;
+}
+
+int mpcb_solve_held_windows_device(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *state,
+                                   const double *v_beta, const double *target, const double *origin,
+                                   const double *threshold, const uint8_t *flags, double *best_cost,
+                                   int64_t *best_index, double *best_traj, double *first_control, int32_t *window_shape) {
+    if (!h || !p) return MPCB_ERR_INVALID;
+    if (N < 0 || N >= (1LL << 31)) return fail(h, MPCB_ERR_INVALID, "N out of range");
+    if (N == 0) return MPCB_OK;
+    if (!state || !v_beta || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
+    int rc = check_window_params(h, p);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    WindowArgs a{};
+    a.p = *p; a.N = N;
+    a.state = state; a.vbeta = v_beta; a.target = target; a.origin = origin; a.threshold = threshold; a.flags = flags;
+    a.out_cost = best_cost; a.out_index = (long long *)best_index; a.out_traj = best_traj; a.out_ctl = first_control;
+    a.out_shape = window_shape;
+    CK(launch_held_windows(h->stream, a, h->sms));
+    h->stats = mpcb_stats{};
+    h->stats.kernel_launches = 1;
+    h->stats.algo = MPCB_ALGO_LEAFWALK;
+    h->stats.units = h->stats.leaves_per_solve = (int64_t)p->n_v * p->n_beta;
+    return MPCB_OK;
+}
+
+int mpcb_solve_held_windows_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *state,
+                                 const double *v_beta, const double *target, const double *origin,
+                                 const double *threshold, const uint8_t *flags, double *best_cost,
+                                 int64_t *best_index, double *best_traj, double *first_control, int32_t *window_shape) {
+    if (!h || !p) return MPCB_ERR_INVALID;
+    if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
+    if (!state || !v_beta || !target || !origin) return fail(h, MPCB_ERR_INVALID, "null input pointer");
+    int rc = check_window_params(h, p);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    // one staging buffer each way: [state 3 | v_beta 2 | target 2 | origin 2 | threshold 1] doubles + flags
+    const size_t per_in = 3 + 2 + 2 + 2 + (threshold ? 1 : 0);
+    const int Hh = p->H;
+    const size_t per_out = 1 + 1 + 3 * (size_t)Hh + 2 + 1;       // cost, index, traj, control, shape (2 x int32)
+    CK(h->small_in.ensure(sizeof(double) * per_in * N + (flags ? N : 0)));
+    CK(h->small_out.ensure(sizeof(double) * per_out * N));
+    double *din = h->small_in.as<double>();
+    size_t off = 0;
+    auto up = [&](const double *src, size_t per) -> const double * {
+        const double *dst = din + off;
+        cudaMemcpyAsync(din + off, src, sizeof(double) * per * N, cudaMemcpyHostToDevice, st);
+        off += per * N;
+        return dst;
+    };
+    const double *d_state = up(state, 3), *d_vb = up(v_beta, 2), *d_target = up(target, 2), *d_origin = up(origin, 2);
+    const double *d_thr = threshold ? up(threshold, 1) : nullptr;
+    const uint8_t *d_flags = nullptr;
+    if (flags) {
+        d_flags = reinterpret_cast<const uint8_t *>(din + off);
+        cudaMemcpyAsync(din + off, flags, N, cudaMemcpyHostToDevice, st);
+    }
+    CK(cudaGetLastError());
+    double *o = h->small_out.as<double>();
+    double *d_cost = o, *d_traj = o + 2 * N, *d_ctl = d_traj + 3 * (size_t)Hh * N;
+    int64_t *d_index = reinterpret_cast<int64_t *>(o + N);
+    int32_t *d_shape = reinterpret_cast<int32_t *>(d_ctl + 2 * N);
+    rc = mpcb_solve_held_windows_device(h, p, N, d_state, d_vb, d_target, d_origin, d_thr, d_flags, d_cost, d_index,
+                                        d_traj, d_ctl, d_shape);
+    if (rc) return rc;
+    if (best_cost) CK(cudaMemcpyAsync(best_cost, d_cost, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (best_index) CK(cudaMemcpyAsync(best_index, d_index, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, st));
+    if (best_traj) CK(cudaMemcpyAsync(best_traj, d_traj, sizeof(double) * 3 * Hh * N, cudaMemcpyDeviceToHost, st));
+    if (first_control) CK(cudaMemcpyAsync(first_control, d_ctl, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, st));
+    if (window_shape) CK(cudaMemcpyAsync(window_shape, d_shape, sizeof(int32_t) * 2 * N, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return MPCB_OK;
 }

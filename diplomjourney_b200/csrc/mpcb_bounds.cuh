@@ -79,7 +79,8 @@ MPCB_HD double lower_bound_from(const LaunchArgs &a, const SolveParams &P, doubl
     }
     const double invl = 1.0 / P.wl;
     projection_range(a, (nx * ch + ny * sh) * invl, fabs(nx * sh - ny * ch) * invl, steps, qlo, qhi);
-    return base0 - kWd * reach + quad_min_range(2.0 * ep, P.wl * qlo, P.wl * qhi) +
+    // a distance cannot become negative: a leaf is no closer to the target than max(0, D - reach)
+    return base0 - kWd * fmin(reach, D) + quad_min_range(2.0 * ep, P.wl * qlo, P.wl * qhi) +
            quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
 }
 

@@ -37,6 +37,9 @@
 #ifndef MPCB_UNROLL4
 #define MPCB_UNROLL4 2  // pairs per unrolled iteration of the four-node loop (1, 2, 4 within 1.3 %)
 #endif
+#ifndef MPCB_PN_CTA2
+#define MPCB_PN_CTA2 512  // threads per CTA of the two-nodes-per-thread pass-1 kernel (one CTA per SM)
+#endif
 #ifndef MPCB_UNROLL
 #define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (4..16 are within 1 %, profiles/r1b_variants.txt)
 #endif
@@ -378,6 +381,53 @@ __device__ __forceinline__ void prefix_min_loop_far2xN(const float4 *__restrict_
     for (int k = 0; k < NPT; ++k) best[k] = b[k];
 }
 
+// SCREENED flavour of the same loop (option "screen", the default of the exhaustive pass 1): every leaf's cost terms are
+// formed exactly as in leaf_val_direct -- dd (scaled squared distance to the target), q (line offset), gg (heading
+// offset) -- but the MUFU.SQRT that turns them into the value L' = sqrt(dd) + q^2 + gg^2 is only spent on nodes that
+// hold a leaf which can still matter.  With cn an upper bound (in the node's direct-form units, error margins
+// included) on the value of any leaf that could be the solve's minimum,
+//      L' < cn   <=>   sqrt(dd) < t,  t = cn - q^2 - gg^2   <=>   t > 0 and t^2 - dd > 0,
+// and fma(t, t, -dd) is correctly rounded, so its sign is that of t^2 - dd for the fp32 t and dd at hand.  The loop
+// keeps the maximum of t^2 - dd over the node's leaves: 9 packed FP32 ops + 1 FMNMX3 per node and leaf pair and no
+// MUFU (against 8 + 2 MUFU.SQRT + 1).  A node whose maximum is positive is re-run through prefix_min_loop_far2 (the
+// values it then publishes are the ones the unscreened kernel publishes); t < 0 with t^2 > dd is a harmless false hit.
+template <bool HEAD, int NPT>
+__device__ __forceinline__ void prefix_screen_loop_far2xN(const float4 *__restrict__ tab, int npairs,
+                                                          const ParentRegs (&p)[NPT], const float (&cn)[NPT],
+                                                          float (&mx)[NPT]) {
+    float2 U[NPT], W[NPT], D[NPT], NU[NPT], NW[NPT], E[NPT], Hh[NPT], C[NPT];
+    float m[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        // negated, so that the last FFMA2 forms t^2 - dd directly
+        U[k] = make_float2(-p[k].u2s, -p[k].u2s); W[k] = make_float2(-p[k].w2s, -p[k].w2s);
+        D[k] = make_float2(-p[k].D2s, -p[k].D2s);
+        NU[k] = make_float2(p[k].nu, p[k].nu); NW[k] = make_float2(p[k].nw, p[k].nw);
+        E[k] = make_float2(p[k].eh, p[k].eh); Hh[k] = make_float2(p[k].nhh, p[k].nhh);
+        C[k] = make_float2(cn[k], cn[k]);
+        m[k] = -INFINITY;
+    }
+    const float2 K2 = make_float2(-kWd2f, -kWd2f);
+    constexpr int kUnroll = NPT == 2 ? MPCB_UNROLL2 : MPCB_UNROLL4;
+#pragma unroll kUnroll
+    for (int i = 0; i < npairs; ++i) {
+        const float4 t0 = tab[2 * i], t1 = tab[2 * i + 1];
+        const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
+        const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const float2 ndd = __ffma2_rn(U[k], A, __ffma2_rn(W[k], B, __ffma2_rn(K2, R, D[k])));      // -dd
+            const float2 q = __ffma2_rn(NU[k], A, __ffma2_rn(NW[k], B, E[k]));
+            float2 t = __ffma2_rn(make_float2(-q.x, -q.y), q, C[k]);
+            if (HEAD) { const float2 gg = __fadd2_rn(G, Hh[k]); t = __ffma2_rn(make_float2(-gg.x, -gg.y), gg, t); }
+            const float2 df = __ffma2_rn(t, t, ndd);
+            m[k] = fmaxf(m[k], fmaxf(df.x, df.y));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) mx[k] = m[k];
+}
+
 // scalar flavour on the same pair table: NEAR regime, or a node sitting exactly on the line origin
 template <bool HEAD>
 __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
@@ -543,10 +593,12 @@ prefix_kernel(const LaunchArgs a) {
 // tiles as prefix_kernel<1>, thread t holding nodes t, t + 1024/NPT, ... of the work item (NPT = 4: two such CTAs per
 // SM).  Same arithmetic per node, so the segment minima (and everything downstream) are bit-identical to the
 // one-node kernel.
-template <bool HEAD, int NPT>
-__global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(const LaunchArgs a) {
+__host__ __device__ constexpr int prefixn_cta(int npt) { return npt == 2 ? MPCB_PN_CTA2 : kPrefixCta / npt; }
+
+template <bool HEAD, int NPT, bool SCREEN = false>
+__global__ void __launch_bounds__(prefixn_cta(NPT), NPT / 2) prefixn_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
-    constexpr int kCta = kPrefixCta / NPT;
+    constexpr int kCta = prefixn_cta(NPT);
     const int tid = threadIdx.x;
     const int S = a.g.S;
     const bool single = S <= kLeafChunk;
@@ -556,7 +608,8 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
         for (int i = tid; i < chunk_f4(S); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
         __syncthreads();
     }
-    constexpr unsigned groups = kPrefixCta / kThreads;
+    constexpr unsigned groups = kCta * NPT / kThreads;           // 256-node tiles per work item
+    static_assert(kCta * NPT % kThreads == 0, "a work item is a whole number of tiles");
     const unsigned long long qps = (a.tiles_per_solve + groups - 1) / groups;
     const unsigned long long nwork = (unsigned long long)a.N * qps;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -568,9 +621,13 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
         ParentRegs pr[NPT] = {};
         bool near[NPT], special[NPT], active[NPT];
         double base[NPT];
-        float best[NPT], Lspecial[NPT];
+        float best[NPT], Lspecial[NPT], cn[NPT];
         unsigned seg[NPT];
         bool all = true;
+        // SCREEN: no leaf whose value exceeds the solve's upper bound (the exact probe, tightened by every node that
+        // found something) by more than the ranking window tol1 can be the minimum or enter the refinement window
+        double ubw = INFINITY;
+        if (SCREEN) ubw = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1;
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
             const unsigned node = tid + k * kCta;
@@ -585,17 +642,27 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
             special[k] = active[k] && origin_case && unmoved;
             if (!(near[k] || special[k])) base[k] = base_direct;
             Lspecial[k] = (float)(P.special - 0.25 * (double)pr[k].e2 * (double)pr[k].e2);
+            cn[k] = SCREEN ? __double2float_ru(ubw - base_direct) : 0.f;
             all = all && active[k] && !near[k] && !special[k];
         }
+        bool hit[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) hit[k] = false;
         for (int c0 = 0; c0 < S; c0 += kLeafChunk) {
-            const int cn = min(kLeafChunk, S - c0);
+            const int cn_ = min(kLeafChunk, S - c0);
             if (!single) {
                 __syncthreads();
-                for (int i = tid; i < chunk_f4(cn); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
+                for (int i = tid; i < chunk_f4(cn_); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
                 __syncthreads();
             }
-            const int npairs = (cn + 1) >> 1;
-            if (all) {
+            const int npairs = (cn_ + 1) >> 1;
+            if (all && SCREEN) {
+                float mx[NPT];
+                prefix_screen_loop_far2xN<HEAD, NPT>(s_leaf, npairs, pr, cn, mx);
+#pragma unroll
+                for (int k = 0; k < NPT; ++k)       // some leaf of the node has t^2 - dd > 0: it may matter
+                    if (mx[k] > 0.f) { best[k] = prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr[k], best[k]); hit[k] = true; }
+            } else if (all) {
                 prefix_min_loop_far2xN<HEAD, NPT>(s_leaf, npairs, pr, best);
             } else {
 #pragma unroll
@@ -605,6 +672,17 @@ __global__ void __launch_bounds__(kPrefixCta / NPT, NPT / 2) prefixn_kernel(cons
                                   ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr[k], near[k], special[k], Lspecial[k], best[k])
                                   : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr[k], best[k]);
                 }
+            }
+        }
+        if (SCREEN) {
+            // a node that found something tightens the solve's upper bound for the work items still to come:
+            // its best fp32 value + the error bound of that value is >= the true cost of a leaf
+            double v = INFINITY;
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) if (hit[k]) v = fmin(v, base[k] + (double)best[k]);
+            if (__any_sync(0xffffffffu, v < INFINITY)) {
+                v = warp_min(v);
+                if ((tid & 31) == 0) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol1));
             }
         }
 #pragma unroll
@@ -684,7 +762,7 @@ __global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchA
 // the pruned pass-1 kernels then walk.  Exactness: same argument as the per-node cut.
 __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, unsigned long long g_begin,
                                                            unsigned long long g_end, unsigned long long *list,
-                                                           unsigned *count) {
+                                                           unsigned *count, unsigned long long list_cap) {
     const unsigned long long g = g_begin + blockIdx.x * (unsigned long long)kThreads + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     bool keep = false;
@@ -714,7 +792,10 @@ __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, u
     unsigned base = 0;
     if (lane == 0 && mk) base = atomicAdd(count, (unsigned)__popc(mk));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) list[base + __popc(mk & ((1u << lane) - 1u))] = g;
+    // every launch tests at most list_cap tiles (one batch), so the list cannot overflow; the guard keeps a future
+    // change of the batching from turning into an out-of-bounds store
+    const unsigned long long slot = (unsigned long long)base + __popc(mk & ((1u << lane) - 1u));
+    if (keep && slot < list_cap) list[slot] = g;
     for (int o = 16; o > 0; o >>= 1) cut_nodes += __shfl_xor_sync(0xffffffffu, cut_nodes, o);
     if (lane == 0 && cut_nodes) atomicAdd(a.counters + 2, (unsigned long long)cut_nodes);
 }
@@ -1293,7 +1374,40 @@ __global__ void finalize_kernel(const LaunchArgs a, double *best_cost, long long
     }
 }
 
+// Split tree (one tree shared by the ranks of a communicator): this rank's best leaf per solve -> 16-byte record ...
+__global__ void split_pack_kernel(const LaunchArgs a, SplitRec *mine) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    mine[n].cost = a.bestJ[n];
+    mine[n].index = a.bestIdx[n];
+}
+
+// ... and, after the all-gather, the lexicographic (cost, index) minimum over the ranks' records becomes the solve's
+// record on EVERY rank (rank r's record of solve n is all[r * N + n]); finalize_kernel then re-rolls the winner's
+// trajectory locally -- no broadcast.  NaN costs never win (math_model.py:195: a NaN cost fails the strict '<').
+__global__ void split_pick_kernel(const LaunchArgs a, const SplitRec *all, int nranks) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    double bJ = INFINITY; long long bj = -1;
+    for (int r = 0; r < nranks; ++r) {
+        const SplitRec rec = all[(size_t)r * a.N + n];
+        if (rec.cost == rec.cost) lex_min(bJ, bj, rec.cost, rec.index);
+    }
+    a.bestJ[n] = bJ;
+    a.bestIdx[n] = bj;
+}
+
 // ------------------------------------------------------------------------------------ launchers
+cudaError_t launch_split_pack(cudaStream_t st, const LaunchArgs &a, SplitRec *mine) {
+    split_pack_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a, mine);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_pick(cudaStream_t st, const LaunchArgs &a, const SplitRec *all, int nranks) {
+    split_pick_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a, all, nranks);
+    return cudaGetLastError();
+}
+
 static inline int grid_for(unsigned long long work, int sms, int per_sm) {
     unsigned long long cap = (unsigned long long)sms * per_sm;
     return (int)(work < cap ? (work ? work : 1) : cap);
@@ -1350,12 +1464,12 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
         if (pass == 1 && a.prune)   // small grids: nodes are cut lane by lane (the queue costs more than it saves there)
             return head ? launch_persistent(prefix_kernel<1, true, true>, a, pass, sm, sms, st)
                         : launch_persistent(prefix_kernel<1, false, true>, a, pass, sm, sms, st);
-        if (pass == 1 && a.npt == 4)
-            return head ? launch_persistent(prefixn_kernel<true, 4>, a, pass, sm, sms, st, kPrefixCta / 4)
-                        : launch_persistent(prefixn_kernel<false, 4>, a, pass, sm, sms, st, kPrefixCta / 4);
-        if (pass == 1 && a.npt == 2)
-            return head ? launch_persistent(prefixn_kernel<true, 2>, a, pass, sm, sms, st, kPrefixCta / 2)
-                        : launch_persistent(prefixn_kernel<false, 2>, a, pass, sm, sms, st, kPrefixCta / 2);
+#define MPCB_PN(NPT_, SCR_)                                                                                      \
+    (head ? launch_persistent(prefixn_kernel<true, NPT_, SCR_>, a, pass, sm, sms, st, prefixn_cta(NPT_))         \
+          : launch_persistent(prefixn_kernel<false, NPT_, SCR_>, a, pass, sm, sms, st, prefixn_cta(NPT_)))
+        if (pass == 1 && a.npt == 4) return a.screen ? MPCB_PN(4, true) : MPCB_PN(4, false);
+        if (pass == 1 && a.npt == 2) return a.screen ? MPCB_PN(2, true) : MPCB_PN(2, false);
+#undef MPCB_PN
         if (pass == 1)
             return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixCta)
                         : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixCta);
@@ -1380,9 +1494,10 @@ cudaError_t launch_frontier_expand(cudaStream_t st, const LaunchArgs &a, int k, 
 }
 
 cudaError_t launch_tilecut(cudaStream_t st, const LaunchArgs &a, unsigned long long g_begin, unsigned long long g_end,
-                           unsigned long long *list, unsigned *count) {
+                           unsigned long long *list, unsigned *count, unsigned long long list_cap) {
+    if (g_end - g_begin > list_cap) return cudaErrorInvalidValue;
     const unsigned long long blocks = (g_end - g_begin + kThreads - 1) / kThreads;
-    tilecut_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(a, g_begin, g_end, list, count);
+    tilecut_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(a, g_begin, g_end, list, count, list_cap);
     return cudaGetLastError();
 }
 

@@ -58,25 +58,102 @@ __device__ __forceinline__ void loop_walk(const mpcb_loop_params &p, double v, d
     }
 }
 
+// Acceleration windows around the current (v, beta) (vector_of_velocities / vector_of_beta_angles,
+// math_model_tree.py:239-256): candidate i is  v + delta_v (i - half_v)  kept if 0 <= . < v_max, resp.
+// beta + delta_beta (i - half_beta)  kept if |.| <= beta_limit -- the same float64 expressions, order preserved.
+// Warp 0 builds the velocity window, warp 1 the angle window (ballot + prefix count compaction, 32 candidates per
+// round); out[0] = nV, out[1] = nB, *vslow = max(min V, v_min) (the slow-down override, :312-316).
+// Needs >= 64 threads; the caller synchronises the CTA afterwards.
+__device__ __forceinline__ void build_windows(const mpcb_loop_params &p, double v, double beta, double *s_V,
+                                              double *s_B, int *out, double *vslow) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp > 1) return;
+    const int n = warp == 0 ? p.n_v : p.n_beta;
+    double *dst = warp == 0 ? s_V : s_B;
+    int count = 0;
+    double vmin = INFINITY;
+    for (int i0 = 0; i0 < n && count < kMaxWin; i0 += 32) {
+        const int i = i0 + lane;
+        double c = 0.0;
+        bool keep = false;
+        if (i < n) {
+            if (warp == 0) {
+                c = __dadd_rn(v, __dmul_rn(p.delta_v, (double)i - p.half_v));
+                keep = !(c < 0.0) && c < p.v_max;
+            } else {
+                c = __dadd_rn(beta, __dmul_rn(p.delta_beta, (double)i - p.half_beta));
+                keep = fabs(c) <= p.beta_limit;
+            }
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        const int slot = count + __popc(mk & ((1u << lane) - 1u));
+        if (keep && slot < kMaxWin) { dst[slot] = c; vmin = fmin(vmin, c); }
+        count = min(count + __popc(mk), kMaxWin);
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        if (lane == 0) { out[0] = count; *vslow = vmin > p.v_min ? vmin : p.v_min; }
+    } else if (lane == 0) {
+        out[1] = count;
+    }
+}
+
+// HELD solve of one robot over the windows in shared memory: candidate c = iv*nB + ib holds (v, beta) for all H
+// steps; block-wide lexicographic (cost, index) minimum, result valid on thread 0.  Contains one CTA barrier.
+__device__ __forceinline__ void held_block_solve(const mpcb_loop_params &p, const LoopCost &cost, const double *s_V,
+                                                 const double *s_tanB, int nV, int nB, bool slow, double vslow,
+                                                 double x0, double y0, double phi0, double *s_J, int *s_j,
+                                                 double &bJ, int &bj) {
+    const int tid = threadIdx.x;
+    const int S = nV * nB;
+    bJ = INFINITY; bj = -1;
+    for (int c = tid; c < S; c += kLoopThreads) {
+        const int iv = c / nB, ib = c - iv * nB;
+        const double v = slow ? vslow : s_V[iv];
+        double x = x0, y = y0, phi = phi0;
+        loop_walk(p, v, s_tanB[ib], x, y, phi, nullptr);
+        lex_min_d(bJ, bj, cost(x, y, phi), c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oJ = __shfl_xor_sync(0xffffffffu, bJ, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        lex_min_d(bJ, bj, oJ, oj);
+    }
+    // (s_J / s_j of the previous solve were consumed before the CTA barriers that every caller has between two solves)
+    if ((tid & 31) == 0) { s_J[tid >> 5] = bJ; s_j[tid >> 5] = bj; }
+    __syncthreads();
+    if (tid == 0)
+        for (int i = 1; i < kLoopThreads / 32; ++i) lex_min_d(bJ, bj, s_J[i], s_j[i]);
+}
+
+__device__ __forceinline__ void load_cost(LoopCost &cost, const double *target, const double *origin, long long n,
+                                          int kind) {
+    cost.xt = target[2 * n]; cost.yt = target[2 * n + 1];
+    cost.ox = origin[2 * n]; cost.oy = origin[2 * n + 1];
+    cost.A = cost.yt - cost.oy; cost.B = cost.xt - cost.ox;
+    cost.C = cost.xt * cost.oy - cost.yt * cost.ox;
+    cost.norm = sqrt(cost.A * cost.A + cost.B * cost.B);
+    cost.theta = atan(cost.xt / cost.yt);
+    cost.kind = kind;
+}
+
 __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs a) {
     __shared__ double s_V[kMaxWin], s_B[kMaxWin], s_tanB[kMaxWin];
     __shared__ double s_J[kLoopThreads / 32];
     __shared__ int s_j[kLoopThreads / 32];
     __shared__ double s_state[5];      // x, y, phi, v, beta fed to the next tick
-    __shared__ int s_ctl[4];           // nV, nB, slow flag, stop flag
+    // nV, nB, slow flag, stop decided at the top of a tick, stop decided at its bottom.  The two stop flags are
+    // separate words: each is rewritten only after every thread has passed at least two CTA barriers since reading it.
+    __shared__ int s_ctl[5];
     __shared__ double s_vslow;
     const mpcb_loop_params &p = a.p;
     const int tid = threadIdx.x;
 
     for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
         LoopCost cost;
-        cost.xt = a.target[2 * n]; cost.yt = a.target[2 * n + 1];
-        cost.ox = a.origin[2 * n]; cost.oy = a.origin[2 * n + 1];
-        cost.A = cost.yt - cost.oy; cost.B = cost.xt - cost.ox;
-        cost.C = cost.xt * cost.oy - cost.yt * cost.ox;
-        cost.norm = sqrt(cost.A * cost.A + cost.B * cost.B);
-        cost.theta = atan(cost.xt / cost.yt);
-        cost.kind = p.cost_kind;
+        load_cost(cost, a.target, a.origin, n, p.cost_kind);
         // thread-0 state of the loop (math_mpc locals and the module globals it touches)
         double thr = a.first_threshold ? a.first_threshold[n] : INFINITY;
         int slow_steps = a.slow_steps ? a.slow_steps[n] : 0;
@@ -84,6 +161,7 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
         bool recursive = false, have_traj = false;
         double opt[3 * MPCB_MAX_H], res_v = 0.0, res_beta = 0.0;
         double xprev = 0.0, yprev = 0.0;
+        __syncthreads();                           // the previous robot's shared state has been consumed
         if (tid == 0) {
             for (int k = 0; k < 5; ++k) s_state[k] = a.init[5 * n + k];
             xprev = s_state[0]; yprev = s_state[1];
@@ -91,29 +169,15 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
         __syncthreads();
 
         for (;;) {
-            // ---- stop test + acceleration windows (thread 0, serial: <= n_v + n_beta candidates)
+            // ---- stop test (thread 0) + acceleration windows (warps 0 and 1)
             if (tid == 0) {
-                const double x = s_state[0], y = s_state[1];
-                const double dx = cost.xt - x, dy = cost.yt - y;
+                const double dx = cost.xt - s_state[0], dy = cost.yt - s_state[1];
                 int stop = 0;
                 if (dx * dx + dy * dy <= p.eps) { stop = 1; status = 0; }
                 else if (ticks >= p.max_ticks) { stop = 1; status = 2; }
-                int nV = 0, nB = 0;
-                if (!stop) {
-                    const double v = s_state[3], beta = s_state[4];
-                    double vmin = INFINITY;
-                    for (int i = 0; i < p.n_v && nV < kMaxWin; ++i) {
-                        const double pv = __dadd_rn(v, __dmul_rn(p.delta_v, (double)i - p.half_v));
-                        if (!(pv < 0.0) && pv < p.v_max) { s_V[nV++] = pv; vmin = fmin(vmin, pv); }
-                    }
-                    for (int i = 0; i < p.n_beta && nB < kMaxWin; ++i) {
-                        const double pa = __dadd_rn(beta, __dmul_rn(p.delta_beta, (double)i - p.half_beta));
-                        if (fabs(pa) <= p.beta_limit) s_B[nB++] = pa;
-                    }
-                    s_vslow = vmin > p.v_min ? vmin : p.v_min;
-                }
-                s_ctl[0] = nV; s_ctl[1] = nB; s_ctl[2] = slow_steps > 0; s_ctl[3] = stop;
+                s_ctl[2] = slow_steps > 0; s_ctl[3] = stop;
             }
+            build_windows(p, s_state[3], s_state[4], s_V, s_B, s_ctl, &s_vslow);
             __syncthreads();
             if (s_ctl[3]) break;
             const int nV = s_ctl[0], nB = s_ctl[1];
@@ -121,30 +185,13 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
             for (int i = tid; i < nB; i += kLoopThreads) s_tanB[i] = tan(s_B[i]);
             __syncthreads();
 
-            // ---- HELD solve: candidate c = iv*nB + ib holds (v, beta) for all H steps
-            const int S = nV * nB;
+            // ---- HELD solve
             const double x0 = s_state[0], y0 = s_state[1], phi0 = s_state[2];
-            double bJ = INFINITY; int bj = -1;
-            for (int c = tid; c < S; c += kLoopThreads) {
-                const int iv = c / nB, ib = c - iv * nB;
-                const double v = slow ? s_vslow : s_V[iv];
-                double x = x0, y = y0, phi = phi0;
-                loop_walk(p, v, s_tanB[ib], x, y, phi, nullptr);
-                const double J = cost(x, y, phi);
-                lex_min_d(bJ, bj, J, c);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double oJ = __shfl_xor_sync(0xffffffffu, bJ, o);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                lex_min_d(bJ, bj, oJ, oj);
-            }
-            if ((tid & 31) == 0) { s_J[tid >> 5] = bJ; s_j[tid >> 5] = bj; }
-            __syncthreads();
+            double bJ; int bj;
+            held_block_solve(p, cost, s_V, s_tanB, nV, nB, slow, s_vslow, x0, y0, phi0, s_J, s_j, bJ, bj);
 
             // ---- apply (thread 0)
             if (tid == 0) {
-                for (int i = 1; i < kLoopThreads / 32; ++i) lex_min_d(bJ, bj, s_J[i], s_j[i]);
                 if (bj >= 0 && bJ < thr) {                  // strict '<' (math_model_tree.py:351)
                     const int iv = bj / nB, ib = bj - iv * nB;
                     res_v = slow ? s_vslow : s_V[iv];
@@ -177,17 +224,79 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
                     else if (rx == xprev && ry == yprev) recursive = true;
                     xprev = rx; yprev = ry;
                 }
-                s_ctl[3] = stop;
+                s_ctl[4] = stop;
             }
             __syncthreads();
-            if (s_ctl[3]) break;
+            if (s_ctl[4]) break;
         }
         if (tid == 0) {
             a.out_ticks[n] = ticks;
             a.out_status[n] = status;
         }
-        __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ONE online tick for a batch of robots that each have their OWN acceleration window: the window
+// is rebuilt per robot and per tick around the robot's current (v, beta) (math_model_tree.py:239-256, called at
+// :543-545 and, with the noisy actuator values, at :590-597), so a batch of robots shares no grid.  One CTA per
+// robot: windows on the device, HELD solve in float64 with the reference's formula, the winner re-rolled -- one
+// launch for the whole batch.  index = iv * nB + ib within the robot's own window (shape returned).
+__global__ void __launch_bounds__(kLoopThreads) held_windows_kernel(const WindowArgs a) {
+    __shared__ double s_V[kMaxWin], s_B[kMaxWin], s_tanB[kMaxWin];
+    __shared__ double s_J[kLoopThreads / 32];
+    __shared__ int s_j[kLoopThreads / 32];
+    __shared__ int s_n[2];
+    __shared__ double s_vslow;
+    const mpcb_loop_params &p = a.p;
+    const int tid = threadIdx.x;
+    for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
+        const int fl = a.flags ? (int)a.flags[n] : 0;
+        double *traj = a.out_traj ? a.out_traj + (size_t)n * 3 * p.H : nullptr;
+        auto none = [&](int nV, int nB) {              // no candidate / entry not to be solved
+            if (a.out_cost) a.out_cost[n] = NAN;
+            if (a.out_index) a.out_index[n] = -1;
+            if (traj) for (int k = 0; k < 3 * p.H; ++k) traj[k] = NAN;
+            if (a.out_ctl) { a.out_ctl[2 * n] = NAN; a.out_ctl[2 * n + 1] = NAN; }
+            if (a.out_shape) { a.out_shape[2 * n] = nV; a.out_shape[2 * n + 1] = nB; }
+        };
+        if (fl & MPCB_FLAG_SKIP) { if (tid == 0) none(0, 0); continue; }
+        LoopCost cost;
+        load_cost(cost, a.target, a.origin, n, p.cost_kind);
+        __syncthreads();                           // the previous robot's windows have been consumed
+        build_windows(p, a.vbeta[2 * n], a.vbeta[2 * n + 1], s_V, s_B, s_n, &s_vslow);
+        __syncthreads();
+        const int nV = s_n[0], nB = s_n[1];
+        for (int i = tid; i < nB; i += kLoopThreads) s_tanB[i] = tan(s_B[i]);
+        __syncthreads();
+        const bool slow = (fl & MPCB_FLAG_SLOW) != 0;
+        const double x0 = a.state[3 * n], y0 = a.state[3 * n + 1], phi0 = a.state[3 * n + 2];
+        double bJ; int bj;
+        held_block_solve(p, cost, s_V, s_tanB, nV, nB, slow, s_vslow, x0, y0, phi0, s_J, s_j, bJ, bj);
+        if (tid == 0) {
+            if (bj < 0) { none(nV, nB); continue; }
+            const double thr = a.threshold ? a.threshold[n] : INFINITY;
+            const int iv = bj / nB, ib = bj - iv * nB;
+            const double v = slow ? s_vslow : s_V[iv];
+            double x = x0, y = y0, phi = phi0, tr[3 * MPCB_MAX_H];
+            loop_walk(p, v, s_tanB[ib], x, y, phi, tr);
+            if (traj) for (int k = 0; k < 3 * p.H; ++k) traj[k] = tr[k];
+            if (a.out_cost) a.out_cost[n] = bJ;
+            if (a.out_index) a.out_index[n] = bJ < thr ? bj : -1;       // strict '<' (math_model_tree.py:351)
+            if (a.out_ctl) { a.out_ctl[2 * n] = v; a.out_ctl[2 * n + 1] = s_B[ib]; }
+            if (a.out_shape) { a.out_shape[2 * n] = nV; a.out_shape[2 * n + 1] = nB; }
+        }
+    }
+}
+
+cudaError_t launch_held_windows(cudaStream_t st, const WindowArgs &a, int sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, held_windows_kernel, kLoopThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    long long grid = (long long)sms * per_sm;
+    if (grid > a.N) grid = a.N;
+    held_windows_kernel<<<(unsigned)grid, kLoopThreads, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -149,6 +149,7 @@ struct LaunchArgs {
     unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes, [3] same, frontier descent (added to [2] when the descent completes)
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
+    int screen;                            // exhaustive prefix pass 1: 0 = MUFU.SQRT per leaf, 1 = screened (sqrt only on nodes that can matter)
     double cosk[kMaxH], sink[kMaxH];       // cos / sin of (i+1) dphi_max: the heading range reachable in i+1 steps (cos = -2: the whole circle)
     // subtree cut (pruned pass 1, H >= 3): tiles that survived the depth-(H-2) bound, as global tile numbers
     // n * tiles_per_solve + tile; null = walk every tile
@@ -170,6 +171,9 @@ struct LaunchArgs {
     unsigned long long dump_begin, dump_count;
 };
 
+// split tree: one rank's (cost, index) record of one solve -- what the ranks all-gather (mpcb_nccl.cu)
+struct __align__(16) SplitRec { double cost; long long index; };
+
 // device-resident closed loop (mpcb_loop.cu)
 struct LoopArgs {
     mpcb_loop_params p;
@@ -178,6 +182,16 @@ struct LoopArgs {
     const int *slow_steps;
     double *out_log;
     int *out_ticks, *out_status;
+};
+
+// one online tick of a batch of robots with per-robot acceleration windows (mpcb_loop.cu); all pointers are device
+struct WindowArgs {
+    mpcb_loop_params p;
+    long long N;
+    const double *state, *vbeta, *target, *origin, *threshold;   // [N][3], [N][2] (current v, beta), [N][2], [N][2], [N] or null
+    const unsigned char *flags;                                   // MPCB_FLAG_* per robot, nullable
+    double *out_cost; long long *out_index; double *out_traj, *out_ctl;
+    int *out_shape;                                               // [N][2] = (nV, nB) of each robot's window, nullable
 };
 
 // per-tick bookkeeping of the FULL closed loop (mpcb_loop.cu)

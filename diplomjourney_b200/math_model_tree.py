@@ -203,18 +203,21 @@ def vector_of_beta_angles(actual_beta):
     return [pa for pa in window if abs(pa) <= (beta_max + math.radians(eps_beta))]
 
 
-def get_actual_velocity(velocity_ref):
-    """Actuator disturbance (math_model_tree.py:259-267)."""
-    if random.random() < 0.7:
+def get_actual_velocity(velocity_ref, rng=None):
+    """Actuator disturbance (math_model_tree.py:259-267).  ``rng``: a numpy RandomState standing in for the
+    module-level generator (one per robot in ``math_mpc_batch``)."""
+    rng = random if rng is None else rng
+    if rng.random() < 0.7:
         if velocity_ref < 0.4:
-            return velocity_ref + (random.randint(0, 5) / 1000)
-        return velocity_ref + (random.randint(-100, 10) / 1000)
+            return velocity_ref + (rng.randint(0, 5) / 1000)
+        return velocity_ref + (rng.randint(-100, 10) / 1000)
     return velocity_ref
 
 
-def get_actual_beta_angle(beta_ref):
-    if random.random() < 0.7:
-        return beta_ref + math.radians(random.randint(-5, 5))
+def get_actual_beta_angle(beta_ref, rng=None):
+    rng = random if rng is None else rng
+    if rng.random() < 0.7:
+        return beta_ref + math.radians(rng.randint(-5, 5))
     return beta_ref
 
 
@@ -234,17 +237,12 @@ def predictive_control(_initial_x, _initial_y, _initial_phi, _target_x, _target_
                        _vector_beta, isActual):
     """One online MPC tick (math_model_tree.py:278-496).  As in the reference, the cost reads the
     module globals x_t, y_t, x_0, y_0 -- the target arguments are not used."""
-    global optimal_trajectory, optimal_criterion, t, m, result_v, result_beta, steps_for_slowing
     g = globals()
-    size_max_1 = np.size(_vector_beta) * np.size(_vector_v)
-
-    t += delta_t
-    (actual_time_arr_for_plotting if isActual else time_arr_for_plotting).append(t)
-
-    slowing = steps_for_slowing > 0
-    if slowing and np.size(_vector_v) == 0:
-        np.min(_vector_v)                       # the reference raises here (math_model_tree.py:313)
-    if size_max_1 > 0:
+    found = None
+    # an empty window has no candidate: the reference's loops do not execute, no leaf improves and the previous
+    # trajectory is handed back (the np.min at math_model_tree.py:313 sits INSIDE the velocity loop)
+    if np.size(_vector_beta) * np.size(_vector_v) > 0:
+        slowing = g["steps_for_slowing"] > 0
         solver = _solver()
         solver.set_grid(_vector_v, _vector_beta, L, delta_t, v_min)
         r = solver.solve(_native.MODE_HELD, _native.COST_TREE, prediction_horizon,
@@ -255,12 +253,24 @@ def predictive_control(_initial_x, _initial_y, _initial_phi, _target_x, _target_
             if not slowing:                      # hand back the caller's own objects where possible
                 k = int(r["index"][0])
                 v_used, beta_used = _vector_v[k // np.size(_vector_beta)], _vector_beta[k % np.size(_vector_beta)]
-            optimal_trajectory = [[[p[0], p[1], p[2], v_used, beta_used] for p in r["traj"][0]]]
-            result_v, result_beta = v_used, beta_used
-            optimal_criterion = r["cost"][0]
-    steps_for_slowing -= 1
+            found = (r["traj"][0], v_used, beta_used, r["cost"][0])
+    return _finish_tick(g, found, isActual)
 
-    best = optimal_trajectory[0]
+
+def _finish_tick(g, found, isActual):
+    """Everything predictive_control does around the tree solve (math_model_tree.py:301-305,361-429), on the state
+    dict ``g``: the module globals for the reference API, one dict per robot for ``math_mpc_batch``.
+    ``found`` = (poses[H][3], v, beta, cost) of a leaf that beat the threshold, or None."""
+    g["t"] += delta_t
+    g["actual_time_arr_for_plotting" if isActual else "time_arr_for_plotting"].append(g["t"])
+    if found is not None:
+        traj, v_used, beta_used, cost = found
+        g["optimal_trajectory"] = [[[p[0], p[1], p[2], v_used, beta_used] for p in traj]]
+        g["result_v"], g["result_beta"] = v_used, beta_used
+        g["optimal_criterion"] = cost
+    g["steps_for_slowing"] -= 1
+
+    best = g["optimal_trajectory"][0]
     poses = [[best[k][c] for k in range(3)] for c in range(3)]          # [x|y|phi][step]
     for names, vals in zip(_log_names(isActual), poses):
         for name, val in zip(names, vals):
@@ -269,27 +279,28 @@ def predictive_control(_initial_x, _initial_y, _initial_phi, _target_x, _target_
     # finishing heuristic (math_model_tree.py:388-414): once the third predicted pose is on target,
     # the next two ticks hand out the second and then the third pose of that tick's prediction
     pick = 0
-    if m == 2:
+    if g["m"] == 2:
         pick = 2
-    elif m == 1:
+    elif g["m"] == 1:
         pick = 1
-        m += 1
-    elif is_on_target(poses[0][2], poses[1][2], x_t, y_t)[0]:
-        m += 1
+        g["m"] += 1
+    elif is_on_target(poses[0][2], poses[1][2], g["x_t"], g["y_t"])[0]:
+        g["m"] += 1
     result_x, result_y, result_phi = poses[0][pick], poses[1][pick], poses[2][pick]
+    result_v, result_beta = g["result_v"], g["result_beta"]
 
     if not isActual:
-        result_trajectory_x.append(result_x)
-        result_trajectory_y.append(result_y)
-        result_trajectory_phi.append(result_phi)
-        result_trajectory_v.append(result_v)
-        result_trajectory_beta.append(result_beta)
-        result_trajectory_angle_speed.append((result_v / L) * np.tan(result_beta))
+        g["result_trajectory_x"].append(result_x)
+        g["result_trajectory_y"].append(result_y)
+        g["result_trajectory_phi"].append(result_phi)
+        g["result_trajectory_v"].append(result_v)
+        g["result_trajectory_beta"].append(result_beta)
+        g["result_trajectory_angle_speed"].append((result_v / L) * np.tan(result_beta))
     else:
-        actual_result_trajectory_x.append(result_x)
-        actual_result_trajectory_y.append(result_y)
-        actual_result_trajectory_phi.append(result_phi)
-    optimal_criterion = sys.maxsize            # the online controller re-arms the threshold every tick
+        g["actual_result_trajectory_x"].append(result_x)
+        g["actual_result_trajectory_y"].append(result_y)
+        g["actual_result_trajectory_phi"].append(result_phi)
+    g["optimal_criterion"] = sys.maxsize       # the online controller re-arms the threshold every tick
     return [result_x, result_y, result_phi, result_v, result_beta]
 
 
@@ -356,15 +367,110 @@ def math_mpc(initial_coordinates, target_coordinates, isActual):
     t = 0
 
 
-def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origin=None, cost_kind=None):
-    """EXTENSION (not in the reference): the closed loop of ``math_mpc(..., isActual=False)`` for a
-    whole batch of robots, executed on the GPU without returning to the host between ticks
-    (one CTA per robot; no scripted operator events).  ``initial_coordinates`` [N][5] =
-    x, y, phi, v, beta; ``target_coordinates`` [N][2].  The tracked line starts at the module's
-    x_0, y_0 unless ``origin`` [N][2] is given.  Returns dict(log[N][max_ticks][5], ticks[N], status[N])."""
+_EVENT_KEYS = ("x_t", "y_t", "x_0", "y_0", "phi_0", "steps_for_slowing")
+
+
+def _robot_events(ctx, tick, px, py, pphi, pv, isActual):
+    """The scripted operator events for ONE robot of a batch: new_target / turn_left / turn_right / slow_down work on
+    the module globals, so the robot's line, target and slow-down counter are swapped in, the event applied, and
+    swapped out again (events are rare: four ticks of a run)."""
+    if tick not in (1, 60, 90, 110):
+        return
+    g = globals()
+    saved = {k: g[k] for k in _EVENT_KEYS}
+    g.update({k: ctx[k] for k in _EVENT_KEYS})
+    try:
+        _scripted_events(tick, px, py, pphi, pv, isActual)
+        ctx.update({k: g[k] for k in _EVENT_KEYS})
+    finally:
+        g.update(saved)
+
+
+def _math_mpc_batch_ticks(ini, tgt, org, first, max_ticks, cost_kind, isActual, rngs, events):
+    """The tick loop of ``math_mpc`` (math_model_tree.py:542-635) for N robots at once: per tick ONE batched device
+    solve in which every robot has its own acceleration window (``mpcb_solve_held_windows``), then the reference's
+    per-robot host bookkeeping -- finishing heuristic, logs, actuator noise drawn from the robot's own generator,
+    stall detection, scripted events."""
     from . import config as _cfg
+    n = ini.shape[0]
     params = _native.LoopParams.from_config(_cfg, _native.COST_TREE if cost_kind is None else cost_kind,
                                             prediction_horizon, max_ticks)
+    robots = []
+    for i in range(n):
+        ctx = {}
+        reset_state(ctx)
+        ctx.update(x_t=tgt[i, 0], y_t=tgt[i, 1], x_0=org[i, 0], y_0=org[i, 1], phi_0=phi_0, optimal_criterion=first[i],
+                   pose=[ini[i, k] for k in range(5)], previous=(ini[i, 0], ini[i, 1]), status=None, ticks=0,
+                   rng=None if rngs is None else rngs[i], out=[])
+        robots.append(ctx)
+    solver = _solver()
+    for _ in range(max_ticks):
+        live = [c for c in robots if c["status"] is None]
+        for c in live:
+            if is_on_target(c["pose"][0], c["pose"][1], c["x_t"], c["y_t"])[0]:
+                c["status"] = _native.LOOP_ON_TARGET
+        live = [c for c in live if c["status"] is None]
+        if not live:
+            break
+        r = solver.solve_held_windows(
+            params, [c["pose"][:3] for c in live], [c["pose"][3:5] for c in live],
+            [[c["x_t"], c["y_t"]] for c in live], [[c["x_0"], c["y_0"]] for c in live],
+            threshold=[float(c["optimal_criterion"]) for c in live],
+            flags=[_native.FLAG_SLOW if c["steps_for_slowing"] > 0 else 0 for c in live])
+        for k, c in enumerate(live):
+            found = None
+            if r["index"][k] >= 0:
+                found = (r["traj"][k], r["first_control"][k, 0], r["first_control"][k, 1], r["cost"][k])
+            elif c["optimal_trajectory"] == [[[0]]]:
+                c["status"] = _native.LOOP_NO_LEAF          # the reference raises IndexError on the placeholder
+                continue
+            px, py, pphi, cv, cb = _finish_tick(c, found, isActual)
+            if isActual:
+                pv, pbeta = get_actual_velocity(cv, c["rng"]), get_actual_beta_angle(cb, c["rng"])
+                c["actual_result_trajectory_v"].append(pv)
+                c["actual_result_trajectory_beta"].append(pbeta)
+                c["actual_result_trajectory_angle_speed"].append((pv / L) * np.tan(pbeta))
+            else:
+                pv, pbeta = cv, cb
+            c["pose"] = [px, py, pphi, pv, pbeta]
+            c["out"].append([px, py, pphi, pv, pbeta])
+            c["ticks"] += 1
+            if c["recursive"]:
+                c["status"] = _native.LOOP_STALLED
+                continue
+            if (px, py) == c["previous"]:
+                c["recursive"] = True
+            if events:
+                _robot_events(c, c["p"], px, py, pphi, pv, isActual)
+            c["previous"] = (px, py)
+            c["p"] += 1
+    log = np.full((n, max_ticks, 5), np.nan)
+    for i, c in enumerate(robots):
+        if c["status"] is None:
+            c["status"] = _native.LOOP_ON_TARGET if is_on_target(c["pose"][0], c["pose"][1], c["x_t"], c["y_t"])[0] \
+                else _native.LOOP_MAX_TICKS
+        if c["out"]:
+            log[i, :len(c["out"])] = c["out"]
+    return dict(log=log, ticks=np.array([c["ticks"] for c in robots], np.int32),
+                status=np.array([c["status"] for c in robots], np.int32), robots=robots)
+
+
+def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origin=None, cost_kind=None,
+                   isActual=False, rngs=None, events=False):
+    """EXTENSION (not in the reference): the closed loop of ``math_mpc`` for a whole batch of robots.
+    ``initial_coordinates`` [N][5] = x, y, phi, v, beta; ``target_coordinates`` [N][2].  The tracked line starts at
+    the module's x_0, y_0 unless ``origin`` [N][2] is given.
+
+    * ``isActual=False, events=False``: executed on the GPU without returning to the host between ticks (one CTA
+      per robot, ``mpcb_held_closed_loop``).
+    * ``isActual=True`` (actuator noise, math_model_tree.py:259-275,590-597; ``rngs`` = one numpy RandomState per
+      robot, default the module generator) and/or ``events=True`` (the demo run's scripted operator events,
+      :564-569,617-624): the host draws the noise and applies the events between ticks, and every tick is ONE batched
+      device solve with per-robot acceleration windows (``mpcb_solve_held_windows``).  The returned dict then also
+      carries ``robots``: per robot the state and log lists of the reference module (``actual_result_trajectory_x`` ...).
+
+    Returns dict(log[N][max_ticks][5], ticks[N], status[N])."""
+    from . import config as _cfg
     ini = np.asarray(initial_coordinates, dtype=np.float64).reshape(-1, 5)
     org = np.array([[x_0, y_0]], dtype=np.float64) if origin is None else np.asarray(origin, np.float64).reshape(-1, 2)
     tgt = np.asarray(target_coordinates, dtype=np.float64).reshape(-1, 2)
@@ -381,12 +487,18 @@ def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origi
             first[i] = control_criterion([org[i, 0], org[i, 1], phi_0])
     finally:
         g.update(x_t=saved[0], y_t=saved[1], x_0=saved[2], y_0=saved[3])
+    if isActual or events:
+        return _math_mpc_batch_ticks(ini, tgt, org, first, max_ticks, cost_kind, isActual, rngs, events)
+    params = _native.LoopParams.from_config(_cfg, _native.COST_TREE if cost_kind is None else cost_kind,
+                                            prediction_horizon, max_ticks)
     return _solver().held_closed_loop(params, ini, tgt, org, first_threshold=first)
 
 
-def reset_state():
-    """(Re)creates the module-level state the reference sets up at math_model_tree.py:638-717."""
-    g = globals()
+def reset_state(g=None):
+    """(Re)creates the state the reference sets up at math_model_tree.py:638-717 -- in the module globals, or in the
+    dict ``g`` (one robot of ``math_mpc_batch``)."""
+    own = g is not None
+    g = globals() if g is None else g
     g.update(t=0, dt=delta_t, time_arr_for_plotting=[0], actual_time_arr_for_plotting=[0],
              optimal_trajectory=[[[0]]], result_v=0, result_beta=0, m=0, steps_for_slowing=0,
              recursive=False, p=1)
@@ -404,7 +516,8 @@ def reset_state():
                  "beta_max_vector", "beta_max_vector_minus", "angle_speed_max_vector",
                  "angle_speed_max_vector_minus"):
         g[name] = []
-    g["optimal_criterion"] = control_criterion([x_0, y_0, phi_0])
+    if not own:
+        g["optimal_criterion"] = control_criterion([x_0, y_0, phi_0])
 
 
 reset_state()

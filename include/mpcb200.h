@@ -46,7 +46,8 @@ typedef enum {
     MPCB_ERR_INVALID = -1,      /* bad argument (null pointer, H out of range, ...) */
     MPCB_ERR_CUDA = -2,         /* CUDA runtime error, see mpcb_last_error */
     MPCB_ERR_NO_GRID = -3,      /* solve before mpcb_set_grid */
-    MPCB_ERR_EMPTY_GRID = -4,   /* nv == 0 or nb == 0 (reference: np.min([]) raises, math_model_tree.py:313) */
+    MPCB_ERR_EMPTY_GRID = -4,   /* mpcb_set_grid with nv == 0 or nb == 0: a tree without candidates (the reference's loops then
+                                   simply do not execute and the previous trajectory is returned, math_model_tree.py:308-361) */
     MPCB_ERR_TOO_LARGE = -5,    /* S^H does not fit in int64 */
     MPCB_ERR_NO_DEVICE = -6,
     MPCB_ERR_NCCL = -7
@@ -100,6 +101,12 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * each node, and only the children of the depth-(H-2) survivors are ever set up; the call then synchronises the stream
  * once to read whether a frontier outgrew "frontier_cap" entries (default 2^22), in which case mode 1 redoes pass 1.
  * 2, default: mode 3 for trees of more than 2^23 tiles per call, mode 1 otherwise.  0: node-level cut only),
+ * "screen" (exhaustive prefix pass 1, i.e. prune = 0; identical results.  1, default: every leaf's cost terms -- scaled
+ * squared distance dd, line offset q, heading offset gg -- are formed, but the MUFU.SQRT that turns them into the value
+ * sqrt(dd) + q^2 + gg^2 is only spent in nodes holding a leaf that can still matter: with cn the largest value a leaf
+ * of the node may have and still beat the solve's upper bound (an exact probe of the S held sequences, tightened by
+ * every node that found something), a leaf matters iff t = cn - q^2 - gg^2 > 0 and fma(t, t, -dd) > 0; such nodes are
+ * re-run with the square roots.  0: one MUFU.SQRT per leaf, no upper bound involved),
  * "nodes_per_thread" (1, 2 or 4, default 2: depth-(H-1) nodes each thread of the exhaustive prefix pass 1 holds --
  * identical results), "dump_direct" (diagnostics: mpcb_dump_leaves_host returns the cheaper fp32 form pass 1 ranks
  * with instead of the one pass 2 filters with; default 0), "frontier_cap" (see "subtree_cut"). */
@@ -195,6 +202,29 @@ MPCB_API int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params
                                  const double *first_threshold, const int32_t *slow_steps,
                                  double *out_log, int32_t *out_ticks, int32_t *out_status);
 
+/* ONE online tick for a batch of robots that each have their OWN acceleration window.  The
+ * reference rebuilds the control window per robot and per tick around the robot's current (v, beta)
+ * (vector_of_velocities / vector_of_beta_angles, math_model_tree.py:239-256, called at :543-545 and -- with the noisy
+ * actuator values of the "actual" run -- at :590-597), so a batch of robots shares no grid and mpcb_set_grid does not
+ * apply: the windows are built on the device from `v_beta` with the same float64 expressions, then every robot's
+ * HELD tree (math_model_tree.py:308-361) is solved in float64, one CTA per robot, ONE launch for the batch.
+ *   p               window constants and horizon (max_ticks is ignored)
+ *   state[N][3], v_beta[N][2] = current (v, beta) of each robot, target[N][2], origin[N][2]
+ *   threshold[N]    NULL = +inf;  flags[N]  MPCB_FLAG_SLOW / MPCB_FLAG_SKIP, NULL = 0
+ * outputs (any may be NULL): as mpcb_solve_batch_*, with best_index = iv * nB + ib inside the robot's own window and
+ *   window_shape[N][2] = (nV, nB) of that window.  An empty window (nV == 0 or nB == 0) has no candidate: index -1,
+ *   cost NaN -- the reference then finds no improving leaf and hands back the previous trajectory. */
+MPCB_API int mpcb_solve_held_windows_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N,
+                                 const double *state, const double *v_beta, const double *target, const double *origin,
+                                 const double *threshold, const uint8_t *flags,
+                                 double *best_cost, int64_t *best_index, double *best_traj, double *first_control,
+                                 int32_t *window_shape);
+MPCB_API int mpcb_solve_held_windows_device(mpcb_handle *h, const mpcb_loop_params *p, int64_t N,
+                                   const double *state, const double *v_beta, const double *target, const double *origin,
+                                   const double *threshold, const uint8_t *flags,
+                                   double *best_cost, int64_t *best_index, double *best_traj, double *first_control,
+                                   int32_t *window_shape);
+
 /* Closed loop of the FULL-tree scripts for a batch of robots (math_model.py:234-254 / run_math_model.py:261-276):
  * every tick solves all still-running robots in ONE batched FULL solve with the CARRIED threshold
  * (optimal_criterion is only lowered by an accepted leaf, math_model.py:195-198), applies the first pose of the
@@ -206,11 +236,31 @@ MPCB_API int mpcb_full_closed_loop_host(mpcb_handle *h, int cost_kind, int H, in
                                const double *target, const double *origin, const double *first_threshold,
                                double eps, int max_ticks, double *out_log, int32_t *out_ticks, int32_t *out_status);
 
-/* Cross-rank reconciliation of a split tree: lexicographic (cost, index) minimum over the
- * ranks of an NCCL communicator (two 8-byte all-reduce-min rounds, exact for float64 costs
- * and 63-bit indices).  comm is an ncclComm_t; cost/index are device pointers (1 element). */
+/* ONE oversized FULL tree per solve, shared by the ranks of an NCCL communicator (one process per GPU): rank r of R
+ * expands the first controls of its contiguous, balanced share of [0, S) -- so rank order is leaf-index order --
+ * and reduces it to a (float64 cost, int64 index) record per solve; ONE collective, an ncclAllGather of those 16-byte
+ * records over NVLink, gives every rank all R of them; a local kernel takes their lexicographic minimum and every
+ * rank re-rolls the winner's trajectory itself (no broadcast).  The only coupling between the leaves of the
+ * reference's tree is the running strict-'<' minimum (math_model.py:195-198); this is its multi-GPU form.
+ * Collective call: every rank of the communicator must make it with the same arguments (N solves, same states);
+ * every rank receives the same outputs, as mpcb_solve_batch_* would return them for the whole tree.  Indices are
+ * global leaf indices.  comm is an ncclComm_t created on the handle's device (mpcb_nccl_comm_create). */
+MPCB_API int mpcb_solve_tree_split_device(mpcb_handle *h, void *nccl_comm, int cost_kind, int H, int64_t N,
+                                 const double *state, const double *target, const double *origin,
+                                 const double *threshold,
+                                 double *best_cost, int64_t *best_index, double *best_traj, double *first_control);
+MPCB_API int mpcb_solve_tree_split_host(mpcb_handle *h, void *nccl_comm, int cost_kind, int H, int64_t N,
+                               const double *state, const double *target, const double *origin,
+                               const double *threshold,
+                               double *best_cost, int64_t *best_index, double *best_traj, double *first_control);
+
+/* The reconciliation step on its own: lexicographic (cost, index) minimum over the ranks of an NCCL communicator,
+ * in place on 1-element device buffers -- one 16-byte all-gather and a local minimum (exact for float64 costs and
+ * 63-bit indices).  Ranks without a leaf (index < 0) or with a NaN cost never win; if no rank holds a leaf the
+ * result is index -1 with the smallest cost reported (NaN if every cost is NaN).  The scratch lives in the handle. */
 MPCB_API int mpcb_allreduce_min(mpcb_handle *h, void *nccl_comm, double *cost_dev, int64_t *index_dev);
-/* NCCL bootstrap helpers (id is 128 bytes, generated on rank 0 and distributed by the caller). */
+/* NCCL bootstrap helpers (id is 128 bytes, generated on rank 0 and distributed by the caller); the communicator
+ * is created on the handle's device. */
 MPCB_API int mpcb_nccl_unique_id(void *id128);
 MPCB_API int mpcb_nccl_comm_create(mpcb_handle *h, int nranks, int rank, const void *id128, void **comm_out);
 MPCB_API int mpcb_nccl_comm_destroy(void *comm);

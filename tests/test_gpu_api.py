@@ -172,3 +172,70 @@ def test_integration_md_stub_runs_verbatim(golden):
     cost, k, traj, ctl = ns["_gpu_held_solve"](c["state"], c["vector_v"], c["vector_beta"], c["slow"], 1e300)
     assert k >= 0
     np.testing.assert_allclose(list(traj[0]) + list(ctl), c["ret"], rtol=0, atol=1e-12)
+
+
+def test_held_windows_batch_equals_per_robot_solves():
+    """mpcb_solve_held_windows: one launch for a batch of robots that each have their own acceleration window
+    (math_model_tree.py:239-256) == the reference flow robot by robot (window lists built on the host, set_grid +
+    HELD solve), bit for bit, and == the float64 oracle.  Covers clipped windows (v near 0 and v_max, beta at the
+    limit), the slow-down override, thresholds that reject, skipped entries and an empty velocity window."""
+    from oracle import closed_form as C
+    nat, params = _window_params()
+    mt = importlib.import_module("diplomjourney_b200.math_model_tree")
+    s = nat.Solver(0)
+    rng = np.random.default_rng(4)
+    n = 96
+    sc = C.random_scenarios(n, 31)
+    vb = np.stack([rng.uniform(0.0, 0.995, n), rng.uniform(-1.05, 1.05, n)], 1)
+    vb[0] = (0.0, 0.0); vb[1] = (0.999, 1.04); vb[2] = (0.01, -1.047); vb[3] = (1.2, 0.0)      # [3]: empty velocity window
+    flags = np.zeros(n, np.uint8); flags[5:20:3] = nat.FLAG_SLOW; flags[7] = nat.FLAG_SKIP
+    thr = np.full(n, np.inf); thr[10:14] = 1.0
+    r = s.solve_held_windows(params, sc[:, :3], vb, sc[:, 3:5], sc[:, :2], threshold=thr, flags=flags)
+    for i in range(n):
+        V, B = mt.vector_of_velocities(vb[i, 0]), mt.vector_of_beta_angles(vb[i, 1])
+        assert tuple(r["shape"][i]) == ((0, 0) if flags[i] & nat.FLAG_SKIP else (len(V), len(B))), i
+        if not V or not B or flags[i] & nat.FLAG_SKIP:
+            assert r["index"][i] == -1 and np.isnan(r["cost"][i])
+            continue
+        s.set_grid(V, B, params.L, params.delta_t, params.v_min)
+        one = s.solve(nat.MODE_HELD, nat.COST_TREE, 3, sc[i, :3], sc[i, 3:5], sc[i, :2], threshold=thr[i],
+                      flags=int(flags[i]))
+        assert r["index"][i] == one["index"][0] and r["cost"][i] == one["cost"][0], i
+        np.testing.assert_array_equal(r["traj"][i], one["traj"][0])
+        np.testing.assert_array_equal(r["first_control"][i], one["first_control"][0])
+        o = C.solve_held(sc[i, :3], sc[i, 3:5], sc[i, :2], V, B, 3, C.COST_TREE, threshold=thr[i],
+                         slow=bool(flags[i] & nat.FLAG_SLOW), v_min=params.v_min)
+        assert r["index"][i] == o["index"] and r["cost"][i] == pytest.approx(o["cost"], rel=1e-12)
+    assert 3 in [i for i in range(n) if r["shape"][i][0] == 0]
+    s.close()
+
+
+def test_actual_mode_batch_matches_reference_seeded_runs(golden):
+    """Row f2/f3 on the device: N seeded actual-mode robots (actuator noise, operator events) in ONE batch -- one
+    mpcb_solve_held_windows launch per tick -- equal the reference's own seeded runs (held_actual.json) and a
+    sequential math_mpc(..., True) run of the module."""
+    from test_host_api import _actual_batch_equals_fixture_and_sequential
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    mt._backend = None
+    _actual_batch_equals_fixture_and_sequential(mt, golden)
+
+
+def test_device_closed_loop_many_robots_per_cta():
+    """More robots than resident CTAs: every CTA runs several robots back to back (the stop flags of one robot's loop
+    must not leak into the next).  4,096 robots == the same robots in batches of 64."""
+    nat, params = _window_params(max_ticks=256)
+    rng = np.random.default_rng(0)
+    n = 4096
+    init = np.zeros((n, 5)); init[:, 2] = rng.uniform(-1, 1, n)
+    ang = init[:, 2] + rng.uniform(-0.5, 0.5, n); d = rng.uniform(0.05, 1.0, n)
+    tgt = np.stack([d * np.cos(ang), d * np.sin(ang)], 1)
+    s = nat.Solver(0)
+    big = s.held_closed_loop(params, init, tgt, [[0.0, 0.0]], first_threshold=1e10)
+    for lo in range(0, n, 1024):
+        part = s.held_closed_loop(params, init[lo:lo + 64], tgt[lo:lo + 64], [[0.0, 0.0]], first_threshold=1e10)
+        np.testing.assert_array_equal(big["ticks"][lo:lo + 64], part["ticks"])
+        np.testing.assert_array_equal(big["status"][lo:lo + 64], part["status"])
+        np.testing.assert_array_equal(big["log"][lo:lo + 64], part["log"])      # rows past a robot's last tick are NaN
+    assert set(np.unique(big["status"])) <= {nat.LOOP_ON_TARGET, nat.LOOP_STALLED}
+    assert np.isnan(big["log"][0, big["ticks"][0]:]).all() and not np.isnan(big["log"][0, :big["ticks"][0]]).any()
+    s.close()

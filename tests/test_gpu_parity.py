@@ -485,3 +485,43 @@ def test_several_nodes_per_thread_is_bit_identical(solver, cost):
         solver.set_option("nodes_per_thread", 2)                       # library default
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_screened_pass1_is_exact(solver, cost):
+    """option screen=1 (default of the exhaustive prefix pass 1: the MUFU.SQRT of a leaf is only spent in nodes that
+    hold a leaf which can still matter, against the probe's upper bound) returns the records of screen=0 and of the
+    oracle: ragged tiles, a robot on its line origin, one next to its target (NEAR), zero-velocity exact ties, a
+    chunked table (S > 1024), first-control ranges (a range whose held sequences give no bound at all included) and
+    carried thresholds."""
+    grids = [(np.linspace(0.0, 1.0, 11), np.linspace(-1.0, 1.0, 13), 3, 8),
+             (C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0), 3, 6),
+             (C.vector_of_velocities(0.01), C.vector_of_beta_angles(0.9), 3, 4),       # clipped window with v = 0 rows
+             (np.linspace(0.1, 1.0, 30), np.linspace(-1.0, 1.0, 41), 2, 5),           # S = 1230: two table chunks
+             (np.linspace(0.0, 1.0, 6), np.linspace(-1.0, 1.0, 7), 4, 4)]
+    solver.set_option("algo", nat.ALGO_PREFIX)
+    solver.set_option("prune", 0)
+    try:
+        for V, B, H, n in grids:
+            solver.set_grid(V, B, L, DT, VMIN)
+            S = len(V) * len(B)
+            sc = C.random_scenarios(n, 1200 + H + S)
+            sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]                   # next to its target
+            sc[1, 3:5] = sc[1, :2] + [0.0, 1e-3]                    # the optimum stands still: exact ties
+            thr = np.full(n, np.inf); thr[2] = 1.0                  # nothing beats this one
+            for rng_ in (None, (0, max(1, S // 3)), (S // 2, S // 2 + 1)):
+                res = []
+                for scr in (0, 1):
+                    solver.set_option("screen", scr)
+                    res.append(solver.solve(nat.MODE_FULL, COSTS[cost], H, sc[:, :3], sc[:, 3:5], sc[:, :2], threshold=thr,
+                                            i0_range=rng_))
+                for k in ("index", "cost", "traj", "first_control"):
+                    np.testing.assert_array_equal(res[1][k], res[0][k], err_msg=f"{k} S={S} H={H} range={rng_}")
+                if rng_ is None and S ** H <= 3e7:
+                    for i, s_ in enumerate(sc):
+                        o = K.solve_full(s_[:3], s_[3:], s_[:2], V, B, H, cost, threshold=thr[i])
+                        assert res[1]["index"][i] == o["index"], (S, H, i)
+    finally:
+        solver.set_option("screen", 1)
+        solver.set_option("prune", 1)
+        solver.set_option("algo", nat.ALGO_AUTO)

@@ -148,3 +148,80 @@ def test_tree_module_actual_mode_on_oracle_backend(golden):
         assert got.shape == (len(ref),), key
         np.testing.assert_allclose(got, ref, rtol=0, atol=1e-9, err_msg=key)
     assert (mt.p, mt.m, mt.recursive) == (c["p"], c["m"], c["recursive"])
+
+
+def _actual_batch_equals_fixture_and_sequential(mt, golden):
+    """math_mpc_batch(..., isActual=True, events=True): the reference's seeded actual-mode runs as ONE batch (per-robot
+    generators, per-robot operator events, one batched device solve per tick) -- equal to the reference's own logs and
+    to the same robots run one after the other through math_mpc(..., True)."""
+    cases = golden("held_actual")["cases"]
+    seeds = [c["seed"] for c in cases] + [23]
+    n = len(seeds)
+    batch = mt.math_mpc_batch([[0, 0, 0, 0, 0]] * n, [[2, 3]] * n, max_ticks=400, origin=[[0, 0]] * n, isActual=True,
+                              rngs=[np.random.RandomState(s) for s in seeds], events=True)
+    keys = ("actual_result_trajectory_x", "actual_result_trajectory_y", "actual_result_trajectory_phi",
+            "actual_result_trajectory_v", "actual_result_trajectory_beta")
+    for i, c in enumerate(cases):
+        rob = batch["robots"][i]
+        for key in keys:
+            np.testing.assert_allclose(np.array(rob[key], dtype=float), c["log"][key], rtol=0, atol=1e-9, err_msg=key)
+        assert (rob["p"], rob["m"], rob["recursive"]) == (c["p"], c["m"], c["recursive"])
+        assert batch["ticks"][i] == c["p"] - 1
+    # the extra robot against a sequential run of the module itself
+    backend = mt._backend
+    mt.x_0, mt.y_0, mt.phi_0 = 0, 0, 0
+    mt.reset_state()
+    mt._backend = backend
+    np.random.seed(seeds[-1])
+    mt.math_mpc([0, 0, 0, 0, 0], [2, 3], True)
+    rob = batch["robots"][-1]
+    for key in keys:
+        np.testing.assert_array_equal(np.array(rob[key], dtype=float), np.array(getattr(mt, key), dtype=float), err_msg=key)
+    assert (rob["p"], rob["m"]) == (mt.p, mt.m)
+    k = batch["ticks"][-1]
+    np.testing.assert_array_equal(batch["log"][-1, :k, 0], np.array(mt.actual_result_trajectory_x[1:], dtype=float))
+
+
+def test_tree_module_actual_batch_on_oracle_backend(golden):
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    mt._backend = OracleBackend()
+    _actual_batch_equals_fixture_and_sequential(mt, golden)
+
+
+def test_tree_module_empty_window_returns_the_previous_trajectory():
+    """An empty velocity window has no candidates: the reference's loops do not execute (its np.min sits inside the
+    velocity loop, math_model_tree.py:312-313), nothing improves and the previous trajectory is handed back."""
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    mt._backend = OracleBackend()
+    first = mt.predictive_control(0.0, 0.0, 0.0, 2, 3, [0.5], [0.0, 0.1], False)
+    mt.steps_for_slowing = 3
+    again = mt.predictive_control(first[0], first[1], first[2], 2, 3, [], [0.0, 0.1], False)
+    assert again == first and mt.steps_for_slowing == 2 and mt._backend.calls == 1
+
+
+def test_full_modules_reset_their_grid_after_the_tree_module_used_the_solver():
+    """The FULL modules cache 'my grid is set'; any other set_grid on the shared solver must invalidate that."""
+    from diplomjourney_b200 import _native
+    rm = importlib.import_module("diplomjourney_b200.run_math_model")
+
+    class Rec(OracleBackend):
+        _owner = None
+        sets = 0
+
+        def set_grid(self, *a, **k):
+            _native.Solver.set_grid  # same contract as the real solver: every set_grid drops the owner mark
+            self._owner = None
+            self.sets += 1
+            super().set_grid(*a, **k)
+
+    b = Rec()
+    rm._backend, rm._grid_key = b, None
+    rm.vector_v, rm.vector_beta = np.array([0.0, 0.5, 1.0]), np.array([-0.5, 0.0, 0.5])
+    rm.reset_scenario(0.0, 0.0, 0.0, 1.0, 2.0)
+    rm.predictive_control(0.0, 0.0, 0.0, 0.0, 1.0, 2.0)
+    rm.predictive_control(0.0, 0.0, 0.0, 0.0, 1.0, 2.0)
+    assert b.sets == 1                                   # cached
+    b.set_grid([0.3], [0.0], 0.5, 0.05, 0.4)             # someone else (the tree module) re-grids the shared solver
+    rm.predictive_control(0.0, 0.0, 0.0, 0.0, 1.0, 2.0)
+    assert b.sets == 3 and len(b.grid[0]) == 3           # the FULL module put its own grid back
+    rm._backend, rm._grid_key = None, None

@@ -78,9 +78,10 @@ def _bounds(V, B, H, x, k, cost, want_poses=False):
     rest_iso = _quad_min(2 * e, Q) + heading
     true_min = J.reshape(len(D), -1).min(axis=1)
     poses = (X, Y, P)
+    near = np.minimum(reach, D)                                      # a distance cannot become negative
     if want_poses:
-        return base - 1e4 * reach + rest, true_min, poses, (smax, smin, dmax, wl, wh)
-    return base - 1e4 * reach_iso + rest_iso, base - 1e4 * reach + rest, true_min, J.min()
+        return base - 1e4 * near + rest, true_min, poses, (smax, smin, dmax, wl, wh)
+    return base - 1e4 * reach_iso + rest_iso, base - 1e4 * near + rest, true_min, J.min()
 
 
 GRIDS = {
