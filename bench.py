@@ -215,15 +215,34 @@ def held_metrics(solver, nat, C, device_index):
     V, B = C.vector_of_velocities(0.5), C.vector_of_beta_angles(0.0)
     x = C.random_scenarios(1, 3)[0]
     reps = 300
-    solver.set_grid(V, B, C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
-    solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, x[:3], x[3:5], x[:2])
-    t = time.perf_counter()
-    for _ in range(reps):
-        solver.set_grid(V, B, C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
+    cfgv = (C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
+
+    def per_call(fn):
+        fn()
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t) / reps
+
+    def generic():
+        solver.set_grid(V, B, *cfgv)
         solver.solve(nat.MODE_HELD, nat.COST_TREE, 3, x[:3], x[3:5], x[:2])
-    dt = (time.perf_counter() - t) / reps
+
+    def tick():
+        solver.held_tick(V, B, *cfgv, nat.COST_TREE, 3, x[:3], x[3:5], x[:2])
+
+    dt = per_call(generic)
     out["single_tick_host_api"] = dict(us_per_solve=dt * 1e6, solves_per_s=1.0 / dt, S=len(V) * len(B),
-                                       note="set_grid + solve per tick, host buffers, 1 H2D + 1 kernel + 1 D2H")
+                                       note="Solver.set_grid + Solver.solve per tick (two C calls, numpy marshalling): host "
+                                            "buffers, one launch, one synchronisation")
+    dt = per_call(tick)
+    solver.set_option("zero_copy", 0)
+    dt_staged = per_call(tick)
+    solver.set_option("zero_copy", 1)
+    out["single_tick_c_abi"] = dict(us_per_solve=dt * 1e6, solves_per_s=1.0 / dt, us_per_solve_staged_copies=dt_staged * 1e6,
+                                    note="mpcb_held_tick_host through ctypes (what math_model_tree.predictive_control calls): "
+                                         "window lists + one HELD solve in one C call; inputs and results in mapped pinned "
+                                         "host memory (one launch, one synchronisation, no copy); staged = one copy each way")
     if hasattr(solver, "solve_held_windows"):
         # 1,024 robots with DIFFERENT (v, beta): per-robot acceleration windows built on the device, one launch
         m = 1024

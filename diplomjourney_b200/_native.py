@@ -93,6 +93,8 @@ def load():
     loop = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mpcb_held_closed_loop_host.argtypes = loop
     lib.mpcb_held_closed_loop_device.argtypes = loop
+    lib.mpcb_held_tick_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                        vp, vp, vp, C.c_double, C.c_int, vp, vp, vp, vp]
     win = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mpcb_solve_held_windows_host.argtypes = win
     lib.mpcb_solve_held_windows_device.argtypes = win
@@ -133,6 +135,7 @@ class Solver:
         self.S = 0
         self.grid = None
         self._owner = None
+        self._tick = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -232,6 +235,32 @@ class Solver:
         self._ck(self.lib.mpcb_solve_tree_split_device(self.h, comm.comm, cost, H, int(N), vp(state), vp(target),
                                                        vp(origin), vp(threshold), vp(out_cost), vp(out_index),
                                                        vp(out_traj), vp(out_ctl)))
+
+    def held_tick(self, vector_v, vector_beta, L, delta_t, v_min, cost, H, state, target, origin, threshold=math.inf,
+                  flags=0):
+        """One online tick in one call (mpcb_held_tick_host): the control window lists of this tick and ONE HELD
+        solve.  The lean path of math_model_tree.predictive_control: preallocated buffers, no per-call numpy work
+        beyond turning the two window lists into arrays.  Returns (cost, index, traj[H,3], (v, beta))."""
+        buf = self._tick
+        if buf is None or buf["H"] != H:
+            buf = self._tick = dict(H=H, inp=np.empty(7), cost=np.empty(1), index=np.empty(1, np.int64),
+                                    traj=np.empty((H, 3)), ctl=np.empty(2))
+            buf["ptr"] = tuple(C.c_void_p(buf[k].ctypes.data) for k in ("cost", "index", "traj", "ctl"))
+            base = buf["inp"].ctypes.data
+            buf["in_ptr"] = (C.c_void_p(base), C.c_void_p(base + 24), C.c_void_p(base + 40))
+        v = np.asarray(vector_v, dtype=np.float64)
+        b = np.asarray(vector_beta, dtype=np.float64)
+        inp = buf["inp"]
+        inp[0], inp[1], inp[2] = state[0], state[1], state[2]
+        inp[3], inp[4] = target[0], target[1]
+        inp[5], inp[6] = origin[0], origin[1]
+        self._ck(self.lib.mpcb_held_tick_host(self.h, C.c_void_p(v.ctypes.data), v.size, C.c_void_p(b.ctypes.data), b.size,
+                                              L, delta_t, v_min, cost, H, *buf["in_ptr"], float(threshold), int(flags),
+                                              *buf["ptr"]))
+        self.S = v.size * b.size
+        self.grid = (v, b, float(L), float(delta_t), float(v_min))
+        self._owner = None
+        return float(buf["cost"][0]), int(buf["index"][0]), buf["traj"], (float(buf["ctl"][0]), float(buf["ctl"][1]))
 
     def solve_held_windows(self, params: "LoopParams", state, v_beta, target, origin, threshold=None, flags=None):
         """One online tick of N robots, each with its OWN acceleration window built on the device around its current

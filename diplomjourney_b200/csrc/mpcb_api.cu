@@ -29,12 +29,14 @@ cudaError_t launch_tilecut(cudaStream_t, const LaunchArgs &, unsigned long long 
 cudaError_t launch_frontier_expand(cudaStream_t, const LaunchArgs &, int k, const unsigned long long *src,
                                    const unsigned *src_count, unsigned long long *dst, unsigned *dst_count,
                                    unsigned *overflow, int sms);
+cudaError_t launch_tilewalk_fallback(cudaStream_t, const LaunchArgs &, unsigned long long all_tiles, int sms);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
 cudaError_t launch_held_small(cudaStream_t, const SmallArgs &);
 cudaError_t launch_full_apply(cudaStream_t, const FullLoopArgs &);
 cudaError_t launch_held_windows(cudaStream_t, const WindowArgs &, int sms);
+cudaError_t launch_split_ub_min(cudaStream_t, const LaunchArgs &, const unsigned long long *all, int nranks);
 cudaError_t launch_split_pack(cudaStream_t, const LaunchArgs &, SplitRec *mine);
 cudaError_t launch_split_pick(cudaStream_t, const LaunchArgs &, const SplitRec *all, int nranks);
 bool nccl_available();
@@ -205,7 +207,6 @@ static int ensure_tables(mpcb_handle *h) {
     CK(cudaMemcpyAsync(h->leaf32p.p, l32p.data(), sizeof(float4) * 2 * npairs, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ctl32.p, c32.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ctl32_slow.p, c32s.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
     GridTables &g = h->g;
     g.tab64 = h->tab64.as<double4>(); g.vtab = h->vtab.as<double>();
     g.tab64_slow = h->tab64_slow.as<double4>(); g.vtab_slow = h->vtab_slow.as<double>();
@@ -281,6 +282,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "algo")) h->algo = (int)value;
     else if (!strcmp(name, "refine")) h->refine = value != 0.0;
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
+    else if (!strcmp(name, "zero_copy")) h->zero_copy = value != 0.0;
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
     else if (!strcmp(name, "screen")) h->screen = value != 0.0;
@@ -400,14 +402,22 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
                    h->g.smax, h->g.dphimax, h->tol_scale, h->sp.as<SolveParams>())); ++launches;
     if (a.prune || a.screen) {   // exact upper bound on every solve's minimum from the S held sequences
         CK(launch_probe(h->stream, a, h->sms)); ++launches;
+        if (split_comm) {        // ... of this rank's share: the ranks exchange their bounds (8 bytes per solve and rank)
+            CK(h->nccl_scratch.ensure(sizeof(SplitRec) * (size_t)N * (nranks + 1)));
+            unsigned long long *all = h->nccl_scratch.as<unsigned long long>();
+            if (nccl_allgather_bytes(split_comm, h->ub.p, all, sizeof(unsigned long long) * (size_t)N, h->stream) != MPCB_OK)
+                return fail(h, MPCB_ERR_NCCL, "ncclAllGather failed");
+            CK(launch_split_ub_min(h->stream, a, all, nranks)); ++launches;
+        }
     }
     const unsigned __int128 tiles_all = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
     if (a.total_segs > 0 && a.prune && h->subtree_cut && H >= 3 && tiles_all < ((unsigned __int128)1 << 63)) {
         // Subtree cut.  Tile path: batches of tiles go through the depth-(H-2) bound, pass 1 walks the surviving
         // tiles -- all enqueued, no host synchronisation (every grid is persistent over a device-side count).
         // Frontier descent (trees of more than one tile batch, where testing every tile is itself the cost):
-        // survivors of depth k expand to depth k+1 down to depth H-2 and pass 1 walks their children; the host then
-        // reads ONE flag -- did a frontier outgrow its list? -- and only in that case runs the tile path instead.
+        // survivors of depth k expand to depth k+1 down to depth H-2 and pass 1 walks their children; if a frontier
+        // outgrew its list, pass 1 returns at once and a fused tile walk (tilewalk_fallback_kernel) takes over --
+        // a device-side decision, nothing is read back.
         const unsigned long long all = (unsigned long long)tiles_all;
         const unsigned long long batch = std::min<unsigned long long>(all, kTileBatch);
         unsigned long long deepest = 0;                       // N * S^(H-2): the last frontier if nothing is cut
@@ -435,10 +445,10 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
             a.q_count = q_counts + ((H - 3) & 1);
             CK(launch_pass(h->stream, a, 1, pl.prefix, h->sms)); ++launches;
             a.q_list = nullptr; a.q_count = nullptr; a.gate = 0;
-            unsigned overflowed = 0;
-            CK(cudaMemcpyAsync(&overflowed, q_overflow, sizeof overflowed, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            tiles_needed = overflowed != 0;
+            // a frontier that outgrew its list: the fused tile walk redoes pass 1 -- decided on the device, the kernel
+            // returns at once otherwise; the host never reads the flag
+            CK(launch_tilewalk_fallback(h->stream, a, all, h->sms)); ++launches;
+            tiles_needed = false;
         }
         if (tiles_needed) {
             a.tile_list = lists;
@@ -531,16 +541,26 @@ static int solve_held_small(mpcb_handle *h, int cost_kind, int H, int64_t N, con
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMallocHost(&p, bytes * 2);
+        cudaError_t e = cudaHostAlloc(&p, bytes * 2, cudaHostAllocMapped);
         if (e == cudaSuccess) cap = bytes * 2;
         return e;
     };
     CK(pinned(h->pin_in, h->pin_in_cap, n_in * 8));
     CK(pinned(h->pin_out, h->pin_out_cap, n_out * 8));
-    CK(h->small_in.ensure(n_in * 8));
-    CK(h->small_out.ensure(n_out * 8));
+    // A tick of a few robots moves a few hundred bytes each way: the kernel reads its inputs from, and writes its
+    // results to, MAPPED pinned host memory -- one launch and one synchronisation, no copy engine (option "zero_copy").
+    // Bigger batches are staged through device buffers with one copy each way.
+    const bool zero_copy = h->zero_copy && N <= 64;
+    void *zin = nullptr, *zout = nullptr;
+    if (zero_copy) {
+        CK(cudaHostGetDevicePointer(&zin, h->pin_in, 0));
+        CK(cudaHostGetDevicePointer(&zout, h->pin_out, 0));
+    } else {
+        CK(h->small_in.ensure(n_in * 8));
+        CK(h->small_out.ensure(n_out * 8));
+    }
     double *w = (double *)h->pin_in;
-    const double *d = h->small_in.as<double>();
+    const double *d = zero_copy ? (const double *)zin : h->small_in.as<double>();
     SmallArgs a{};
     auto put = [&](const double *src, size_t cnt) { const double *dev = d + (w - (double *)h->pin_in); memcpy(w, src, cnt * 8); w += cnt; return dev; };
     a.v = put(h->hv.data(), nv);
@@ -553,13 +573,13 @@ static int solve_held_small(mpcb_handle *h, int cost_kind, int H, int64_t N, con
         a.flags = d + (w - (double *)h->pin_in);
         for (int64_t i = 0; i < N; ++i) *w++ = (double)(flags[i] & (MPCB_FLAG_SLOW | MPCB_FLAG_SKIP));
     }
-    double *o = h->small_out.as<double>();
+    double *o = zero_copy ? (double *)zout : h->small_out.as<double>();
     a.out_cost = o; a.out_index = (long long *)(o + N); a.out_traj = o + 2 * N; a.out_ctl = o + 2 * N + 3 * (size_t)H * N;
     a.L = h->L; a.delta_t = h->delta_t; a.v_slow = h->v_slow;
     a.nv = (int)nv; a.nb = (int)nb; a.H = H; a.cost_kind = cost_kind; a.N = N;
-    CK(cudaMemcpyAsync(h->small_in.p, h->pin_in, n_in * 8, cudaMemcpyHostToDevice, st));
+    if (!zero_copy) CK(cudaMemcpyAsync(h->small_in.p, h->pin_in, n_in * 8, cudaMemcpyHostToDevice, st));
     CK(launch_held_small(st, a));
-    CK(cudaMemcpyAsync(h->pin_out, h->small_out.p, n_out * 8, cudaMemcpyDeviceToHost, st));
+    if (!zero_copy) CK(cudaMemcpyAsync(h->pin_out, h->small_out.p, n_out * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const double *r = (const double *)h->pin_out;
     if (best_cost) memcpy(best_cost, r, 8 * (size_t)N);
@@ -638,6 +658,17 @@ int mpcb_solve_batch_host(mpcb_handle *h, int mode, int cost_kind, int H, int64_
                                 best_traj, first_control);
     return solve_host_staged(h, mode, cost_kind, H, N, state, target, origin, threshold, flags, i0_begin, i0_end,
                              best_cost, best_index, best_traj, first_control, nullptr);
+}
+
+int mpcb_held_tick_host(mpcb_handle *h, const double *v, int nv, const double *beta, int nb, double L, double delta_t,
+                        double v_min, int cost_kind, int H, const double *state, const double *target,
+                        const double *origin, double threshold, int flags, double *best_cost, int64_t *best_index,
+                        double *best_traj, double *first_control) {
+    int rc = mpcb_set_grid(h, v, nv, beta, nb, L, delta_t, v_min);
+    if (rc) return rc;
+    const uint8_t fl = (uint8_t)flags;
+    return mpcb_solve_batch_host(h, MPCB_MODE_HELD, cost_kind, H, 1, state, target, origin, &threshold, &fl, 0, -1,
+                                 best_cost, best_index, best_traj, first_control);
 }
 
 int mpcb_solve_tree_split_host(mpcb_handle *h, void *nccl_comm, int cost_kind, int H, int64_t N, const double *state,

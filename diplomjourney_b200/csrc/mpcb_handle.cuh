@@ -46,6 +46,7 @@ struct mpcb_handle_s {
     int algo = MPCB_ALGO_AUTO;
     int refine = 1;
     int small_path = 1;
+    int zero_copy = 1;    // small_path with <= 64 solves: inputs and results in mapped pinned host memory, no copies
     int dump_direct = 0;  // mpcb_dump_leaves_host, prefix: dump the values pass 1 ranks with
     int npt = 2;          // exhaustive prefix pass 1: nodes per thread (2: +6 %, tools/ubench)
     unsigned long long frontier_cap = mpcb::kFrontierCap;   // entries per frontier list (option, diagnostics: a tiny value forces the fallback)

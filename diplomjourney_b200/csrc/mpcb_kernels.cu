@@ -38,7 +38,9 @@
 #define MPCB_UNROLL4 2  // pairs per unrolled iteration of the four-node loop (1, 2, 4 within 1.3 %)
 #endif
 #ifndef MPCB_PN_CTA2
-#define MPCB_PN_CTA2 512  // threads per CTA of the two-nodes-per-thread pass-1 kernel (one CTA per SM)
+#define MPCB_PN_CTA2 640  // threads per CTA of the two-nodes-per-thread pass-1 kernel (one CTA per SM, five 256-node tiles per
+                          // work item, 96 registers): 512 / 640 / 768 / 896 / 1024 threads = 2.99 / 3.10 / 2.96 / 2.98 / 2.97e12
+                          // rollouts/s on the cfg2 bench (profiles/r2c_variants.txt, r2f_variants.txt)
 #endif
 #ifndef MPCB_UNROLL
 #define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (4..16 are within 1 %, profiles/r1b_variants.txt)
@@ -760,6 +762,31 @@ __global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchA
 // such q exceeds the solve's running upper bound, no node of the tile can hold a leaf inside the refinement window
 // and the tile never reaches pass 1 (no set-up of its 256 nodes).  Survivors go to a list of global tile numbers that
 // the pruned pass-1 kernels then walk.  Exactness: same argument as the per-node cut.
+// does 256-node tile g (global tile number n * tiles_per_solve + tile) survive the depth-(H-2) bound?
+__device__ __forceinline__ bool tile_survives(const LaunchArgs &a, unsigned long long g, unsigned &cut_nodes) {
+    const unsigned long long n = g / a.tiles_per_solve, tile = g - n * a.tiles_per_solve;
+    const SolveParams &P = a.sp[n];
+    cut_nodes = 0;
+    if (P.flags & kFlagSkip) return false;
+    const unsigned long long S = (unsigned long long)a.g.S;
+    const unsigned long long p_lo = a.u_begin + tile * kThreads;
+    const unsigned long long p_hi = min(p_lo + (unsigned long long)kThreads, a.u_end);     // exclusive
+    const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
+    bool keep = false;
+    for (unsigned long long q = p_lo / S; q <= (p_hi - 1) / S && !keep; ++q) {
+        double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
+        unsigned long long rem = q;
+        for (int k = 0; k < a.H - 2; ++k) {           // fd[k + 2].d = S^(H-3-k): digits of a depth-(H-2) node
+            unsigned long long i = a.fd[k + 2].div(rem);
+            rem -= i * a.fd[k + 2].d;
+            walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
+        }
+        keep = !(subtree_lower_bound(a, P, xi, eta, psi, cp, sp, 2) > bound);      // NaN bounds never cut
+    }
+    if (!keep) cut_nodes = (unsigned)(p_hi - p_lo);
+    return keep;
+}
+
 __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, unsigned long long g_begin,
                                                            unsigned long long g_end, unsigned long long *list,
                                                            unsigned *count, unsigned long long list_cap) {
@@ -767,27 +794,7 @@ __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, u
     const unsigned lane = threadIdx.x & 31u;
     bool keep = false;
     unsigned cut_nodes = 0;
-    if (g < g_end) {
-        const unsigned long long n = g / a.tiles_per_solve, tile = g - n * a.tiles_per_solve;
-        const SolveParams &P = a.sp[n];
-        if (!(P.flags & kFlagSkip)) {
-            const unsigned long long S = (unsigned long long)a.g.S;
-            const unsigned long long p_lo = a.u_begin + tile * kThreads;
-            const unsigned long long p_hi = min(p_lo + (unsigned long long)kThreads, a.u_end);     // exclusive
-            const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
-            for (unsigned long long q = p_lo / S; q <= (p_hi - 1) / S && !keep; ++q) {
-                double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
-                unsigned long long rem = q;
-                for (int k = 0; k < a.H - 2; ++k) {           // fd[k + 2].d = S^(H-3-k): digits of a depth-(H-2) node
-                    unsigned long long i = a.fd[k + 2].div(rem);
-                    rem -= i * a.fd[k + 2].d;
-                    walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
-                }
-                keep = !(subtree_lower_bound(a, P, xi, eta, psi, cp, sp, 2) > bound);      // NaN bounds never cut
-            }
-            if (!keep) cut_nodes = (unsigned)(p_hi - p_lo);
-        }
-    }
+    if (g < g_end) keep = tile_survives(a, g, cut_nodes);
     const unsigned mk = __ballot_sync(0xffffffffu, keep);
     unsigned base = 0;
     if (lane == 0 && mk) base = atomicAdd(count, (unsigned)__popc(mk));
@@ -798,6 +805,86 @@ __global__ void __launch_bounds__(kThreads) tilecut_kernel(const LaunchArgs a, u
     if (keep && slot < list_cap) list[slot] = g;
     for (int o = 16; o > 0; o >>= 1) cut_nodes += __shfl_xor_sync(0xffffffffu, cut_nodes, o);
     if (lane == 0 && cut_nodes) atomicAdd(a.counters + 2, (unsigned long long)cut_nodes);
+}
+
+// Fallback of the frontier descent, decided ON THE DEVICE: when a frontier outgrew its list (*q_overflow != 0), this
+// kernel redoes pass 1 over all tiles -- tile bound and pruned pass 1 fused, no list in global memory, no host in the
+// loop; when it did not, the kernel returns at once (the price of never synchronising: one empty launch).
+// Work item = 256 consecutive tiles: every thread tests one tile (as tilecut_kernel does), the survivors are compacted
+// into shared memory, then the CTA runs the pruned pass 1 on each of them (node-level cut lane by lane, pair loop,
+// segment minimum, upper-bound tightening) -- the arithmetic of prefix_kernel<1, HEAD, true>.
+template <bool HEAD>
+__global__ void __launch_bounds__(kThreads, 4) tilewalk_fallback_kernel(const LaunchArgs a, unsigned long long all_tiles) {
+    if (*(volatile const unsigned *)a.q_overflow == 0) return;
+    extern __shared__ float4 s_leaf[];
+    __shared__ unsigned long long s_tiles[kThreads];
+    __shared__ unsigned s_warp[kThreads / 32];
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, warp = tid >> 5;
+    const int S = a.g.S;
+    const bool single = S <= kLeafChunk;
+    const float4 *__restrict__ gtab = a.g.leaf32p;
+    auto chunk_f4 = [&](int cn) { return 2 * ((cn + 1) >> 1); };
+    if (single) {
+        for (int i = tid; i < chunk_f4(S); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid == 0) a.counters[3] = 0;          // what the abandoned descent had counted as cut
+    const unsigned long long items = (all_tiles + kThreads - 1) / kThreads;
+    for (unsigned long long w = blockIdx.x; w < items; w += gridDim.x) {
+        const unsigned long long g = w * kThreads + tid;
+        unsigned cut_nodes = 0;
+        const bool keep = g < all_tiles && tile_survives(a, g, cut_nodes);
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();                                          // the previous item's list has been consumed
+        if (lane == 0) s_warp[warp] = __popc(mk);
+        for (int o = 16; o > 0; o >>= 1) cut_nodes += __shfl_xor_sync(0xffffffffu, cut_nodes, o);
+        if (lane == 0 && cut_nodes) atomicAdd(a.counters + 2, (unsigned long long)cut_nodes);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (unsigned i = 0; i < kThreads / 32; ++i) { if (i < warp) before += s_warp[i]; total += s_warp[i]; }
+        if (keep) s_tiles[before + __popc(mk & ((1u << lane) - 1u))] = g;
+        __syncthreads();
+        for (unsigned t = 0; t < total; ++t) {
+            const unsigned long long gt = s_tiles[t];
+            const long long n = (long long)(gt / a.tiles_per_solve);
+            const unsigned long long tile = gt - (unsigned long long)n * a.tiles_per_solve;
+            const unsigned seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
+            const SolveParams &P = a.sp[n];
+            const unsigned long long p = a.u_begin + tile * kThreads + tid;
+            bool active = p < a.u_end;
+            ParentRegs pr = {};
+            bool near = false, unmoved = false;
+            double base = 0.0, base_direct = 0.0, lb = -INFINITY;
+            if (active) base = parent_setup(a, P, p, pr, near, unmoved, &lb, &base_direct);
+            const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
+            const bool cut = active && lb > bound;
+            const unsigned mc = __ballot_sync(0xffffffffu, cut);
+            if (lane == 0 && mc) atomicAdd(a.counters + 2, (unsigned long long)__popc(mc));
+            active = active && !cut;
+            const bool special = active && (P.flags & kFlagStartIsOrigin) && unmoved;
+            if (!(near || special)) base = base_direct;
+            const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+            float best = INFINITY;
+            const bool any_active = single ? true : (__syncthreads_or(active) != 0);
+            for (int c0 = 0; any_active && c0 < S; c0 += kLeafChunk) {
+                const int cn = min(kLeafChunk, S - c0);
+                if (!single) {
+                    __syncthreads();
+                    for (int i = tid; i < chunk_f4(cn); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
+                    __syncthreads();
+                }
+                if (!active) continue;
+                const int npairs = (cn + 1) >> 1;
+                best = (near || special) ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr, near, special, Lspecial, best)
+                                         : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr, best);
+            }
+            const double v = active ? base + (double)best : INFINITY;
+            const double vw = warp_min(v);
+            if (lane == 0 && vw < INFINITY) atomicMin(a.ub + n, ordered_key(vw + 0.5 * P.tol1));
+            publish_segmin(a, seg, v);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------ prefix, pruned (pass 1)
@@ -969,24 +1056,26 @@ __device__ __forceinline__ float leafwalk_eval(const LaunchArgs &a, const SolveP
 }
 
 // FULL tree, indices < 2^32, horizon HT known: the control digits of the thread's leaf are kept in registers and
-// advanced by kThreads (mixed-radix add with carries) instead of being re-derived by divisions for every leaf.
+// advanced by kThreads (mixed-radix add with carries) instead of being re-derived by divisions for every leaf.  The
+// digits are kept PRE-SCALED as the addresses of their {dphi, s} table entries -- 32-bit shared-window addresses
+// (SMEM: LDS.64 straight from the digit register; a generic pointer costs an LD.E and 64-bit address math) or byte
+// offsets into the global table -- so that a step needs no address arithmetic at all.
 template <bool HEAD, bool SMEM, int HT, bool ORIGIN>
 __device__ __forceinline__ float leafwalk_eval_digits(const SolveParams &P, const ParentRegs &pr,
-                                                      const float2 *__restrict__ ctl, unsigned ctl_shared,
-                                                      const unsigned (&c)[HT], float Lsp) {
+                                                      const float2 *__restrict__ ctl, const unsigned (&c)[HT], float Lsp) {
     float xi = 0.f, eta = 0.f, psi = 0.f;
 #pragma unroll
     for (int k = 0; k < HT; ++k) {
         float2 t;
-        if (SMEM)   // LDS.64 with a 32-bit shared-window address (a generic pointer costs an LD.E and 64-bit address math)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(ctl_shared + c[k] * 8u));
+        if (SMEM)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(c[k]));
         else
-            t = __ldg(ctl + c[k]);
-        psi += t.x;
+            t = __ldg(reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(ctl) + c[k]));
+        psi = k == 0 ? t.x : psi + t.x;
         float sn, cs;
         __sincosf(psi, &sn, &cs);
-        xi = __fmaf_rn(t.y, cs, xi);
-        eta = __fmaf_rn(t.y, sn, eta);
+        xi = k == 0 ? t.y * cs : __fmaf_rn(t.y, cs, xi);
+        eta = k == 0 ? t.y * sn : __fmaf_rn(t.y, sn, eta);
     }
     return leafwalk_score<HEAD, true, ORIGIN ? 1 : 0>(P, pr, xi, eta, psi, Lsp);      // pass 1 only: direct form
 }
@@ -1020,35 +1109,43 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
         for (unsigned long long tile = tile_lo; tile < tile_hi; ++tile) {
             const unsigned long long j0 = a.u_begin + tile * (unsigned long long)(kThreads * kLeafPerThread) + tid;
             if constexpr (PASS == 1 && KIND == 1 && HT > 0) {
-                // digits of j0 once, then +kThreads per leaf
-                unsigned c[HT];
-                unsigned rem32 = (unsigned)j0;
-#pragma unroll
-                for (int d = 0; d < HT; ++d) { c[d] = a.fd32[d].div(rem32); rem32 -= c[d] * a.fd32[d].d; }
+                // digits of j0 once (as table addresses: base + 8 c), then +kThreads per leaf
                 const unsigned S = (unsigned)a.g.S, jend = (unsigned)a.u_end;
-                unsigned j32 = (unsigned)j0;
-                const unsigned ctl_shared = smem ? (unsigned)__cvta_generic_to_shared(ctl) : 0u;
+                const unsigned base = smem ? (unsigned)__cvta_generic_to_shared(ctl) : 0u;
+                const unsigned wrap = base + 8u * S;           // first address past the table
+                unsigned c[HT], step[HT];
+                unsigned rem32 = (unsigned)j0;
                 bool step_low_only = true;                     // uniform: kThreads in base S has one digit
 #pragma unroll
-                for (int d = 0; d < HT - 1; ++d) step_low_only = step_low_only && a.step_digits[d] == 0;
-                // the table's address space, the line-origin special case and the shape of the index step are uniform per
-                // launch or solve: eight loops
-                auto walk = [&](auto SM, auto ORG, auto LOW) {
+                for (int d = 0; d < HT; ++d) {
+                    const unsigned q = a.fd32[d].div(rem32);
+                    rem32 -= q * a.fd32[d].d;
+                    c[d] = base + 8u * q;
+                    step[d] = 8u * a.step_digits[d];
+                    if (d < HT - 1) step_low_only = step_low_only && a.step_digits[d] == 0;
+                }
+                unsigned j32 = (unsigned)j0;
+                // a tile that lies wholly inside the leaf range needs no per-leaf range test
+                const bool whole = j0 + (unsigned long long)(kLeafPerThread - 1) * kThreads < a.u_end;
+                // the table's address space, the line-origin special case, the shape of the index step and the range test
+                // are uniform per launch, solve or tile: sixteen loops
+                auto walk = [&](auto SM, auto ORG, auto LOW, auto WHOLE) {
 #pragma unroll 4
                     for (int k = 0; k < kLeafPerThread; ++k) {
-                        if (j32 >= jend) break;
+                        if (!decltype(WHOLE)::value && j32 >= jend) break;
                         best = fminf(best, leafwalk_eval_digits<HEAD, decltype(SM)::value, HT, decltype(ORG)::value>(
-                                               P, pr, ctl, ctl_shared, c, Lsp));
+                                               P, pr, ctl, c, Lsp));
                         j32 += kThreads;
                         if (decltype(LOW)::value) {
                             // kThreads < S: only the last digit steps; the carry ripples further once in S leaves
-                            unsigned v = c[HT - 1] + a.step_digits[HT - 1];
-                            if (v >= S) {
-                                v -= S;
+                            unsigned v = c[HT - 1] + step[HT - 1];
+                            if (v >= wrap) {
+                                v -= 8u * S;
 #pragma unroll
                                 for (int d = HT - 2; d >= 0; --d) {
-                                    if (++c[d] < S) break;
-                                    c[d] = 0;
+                                    c[d] += 8u;
+                                    if (c[d] < wrap) break;
+                                    c[d] = base;
                                 }
                             }
                             c[HT - 1] = v;
@@ -1056,16 +1153,17 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
                             unsigned carry = 0;
 #pragma unroll
                             for (int d = HT - 1; d >= 0; --d) {
-                                unsigned v = c[d] + a.step_digits[d] + carry;
-                                carry = v >= S ? 1u : 0u;
-                                c[d] = v - (carry ? S : 0u);
+                                unsigned v = c[d] + step[d] + carry;
+                                carry = v >= wrap ? 8u : 0u;
+                                c[d] = v - (carry ? 8u * S : 0u);
                             }
                         }
                     }
                 };
                 using T = std::true_type; using F = std::false_type;
                 const bool org = (P.flags & kFlagStartIsOrigin) != 0;
-                auto pick = [&](auto SM, auto ORG) { if (step_low_only) walk(SM, ORG, T{}); else walk(SM, ORG, F{}); };
+                auto pick2 = [&](auto SM, auto ORG, auto LOW) { if (whole) walk(SM, ORG, LOW, T{}); else walk(SM, ORG, LOW, F{}); };
+                auto pick = [&](auto SM, auto ORG) { if (step_low_only) pick2(SM, ORG, T{}); else pick2(SM, ORG, F{}); };
                 if (smem) { if (org) pick(T{}, T{}); else pick(T{}, F{}); }
                 else      { if (org) pick(F{}, T{}); else pick(F{}, F{}); }
             } else {
@@ -1397,7 +1495,23 @@ __global__ void split_pick_kernel(const LaunchArgs a, const SplitRec *all, int n
     a.bestIdx[n] = bj;
 }
 
+// Split tree, before the descent: every rank's probe bounds the minimum of the WHOLE tree from above (its held
+// sequences are leaves of it), so the ranks share their bounds -- all[r * N + n] = rank r's key of solve n -- and each
+// continues with the smallest.  Without it a rank whose share holds no good leaf prunes against a weak bound.
+__global__ void split_ub_min_kernel(const LaunchArgs a, const unsigned long long *all, int nranks) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    unsigned long long k = a.ub[n];
+    for (int r = 0; r < nranks; ++r) k = min(k, all[(size_t)r * a.N + n]);
+    a.ub[n] = k;
+}
+
 // ------------------------------------------------------------------------------------ launchers
+cudaError_t launch_split_ub_min(cudaStream_t st, const LaunchArgs &a, const unsigned long long *all, int nranks) {
+    split_ub_min_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a, all, nranks);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_split_pack(cudaStream_t st, const LaunchArgs &a, SplitRec *mine) {
     split_pack_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a, mine);
     return cudaGetLastError();
@@ -1499,6 +1613,17 @@ cudaError_t launch_tilecut(cudaStream_t st, const LaunchArgs &a, unsigned long l
     const unsigned long long blocks = (g_end - g_begin + kThreads - 1) / kThreads;
     tilecut_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(a, g_begin, g_end, list, count, list_cap);
     return cudaGetLastError();
+}
+
+cudaError_t launch_tilewalk_fallback(cudaStream_t st, const LaunchArgs &a, unsigned long long all_tiles, int sms) {
+    const size_t sm = prefix_smem(a);
+    const bool head = a.cost_kind == 0;
+    auto go = [&](auto kernel) {
+        const int grid = sms * resident_ctas(kernel, sm, kThreads);
+        kernel<<<grid, kThreads, sm, st>>>(a, all_tiles);
+        return cudaGetLastError();
+    };
+    return head ? go(tilewalk_fallback_kernel<true>) : go(tilewalk_fallback_kernel<false>);
 }
 
 cudaError_t launch_probe(cudaStream_t st, const LaunchArgs &a, int sms) {

@@ -244,16 +244,22 @@ def predictive_control(_initial_x, _initial_y, _initial_phi, _target_x, _target_
     if np.size(_vector_beta) * np.size(_vector_v) > 0:
         slowing = g["steps_for_slowing"] > 0
         solver = _solver()
-        solver.set_grid(_vector_v, _vector_beta, L, delta_t, v_min)
-        r = solver.solve(_native.MODE_HELD, _native.COST_TREE, prediction_horizon,
-                         [_initial_x, _initial_y, _initial_phi], [x_t, y_t], [x_0, y_0],
-                         threshold=optimal_criterion, flags=_native.FLAG_SLOW if slowing else 0)
-        if r["index"][0] >= 0:
-            v_used, beta_used = r["first_control"][0]
+        flags = _native.FLAG_SLOW if slowing else 0
+        if hasattr(solver, "held_tick"):         # the CUDA library: window lists and solve in one C call
+            cost, k, traj, (v_used, beta_used) = solver.held_tick(
+                _vector_v, _vector_beta, L, delta_t, v_min, _native.COST_TREE, prediction_horizon,
+                (_initial_x, _initial_y, _initial_phi), (x_t, y_t), (x_0, y_0), optimal_criterion, flags)
+            traj = traj.copy()
+        else:                                    # a test double with the two-call interface
+            solver.set_grid(_vector_v, _vector_beta, L, delta_t, v_min)
+            r = solver.solve(_native.MODE_HELD, _native.COST_TREE, prediction_horizon,
+                             [_initial_x, _initial_y, _initial_phi], [x_t, y_t], [x_0, y_0],
+                             threshold=optimal_criterion, flags=flags)
+            cost, k, traj, (v_used, beta_used) = r["cost"][0], int(r["index"][0]), r["traj"][0], r["first_control"][0]
+        if k >= 0:
             if not slowing:                      # hand back the caller's own objects where possible
-                k = int(r["index"][0])
                 v_used, beta_used = _vector_v[k // np.size(_vector_beta)], _vector_beta[k % np.size(_vector_beta)]
-            found = (r["traj"][0], v_used, beta_used, r["cost"][0])
+            found = (traj, v_used, beta_used, cost)
     return _finish_tick(g, found, isActual)
 
 

@@ -91,6 +91,8 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
 /* Options: "tol_scale" (candidate-window multiplier, default 1), "algo" (MPCB_ALGO_*),
  * "refine" (1 = float64 re-evaluation of near-minimal leaves, default; 0 = fp32 winner),
  * "small_path" (1 = host-API HELD solves with <= 4096 candidates run as one float64 launch, default),
+ * "zero_copy" (1, default: on that path, up to 64 solves read their inputs from and write their results to mapped
+ * pinned host memory -- one launch and one synchronisation per call, no copy; 0 = one staged copy each way),
  * "prune" (1 = exact branch-and-bound in the prefix kernel: depth-(H-1) nodes whose children provably cannot
  * reach the refinement window of the best leaf are skipped -- a lower bound from the distance to the target, the
  * steering and speed limits and the most favourable line / heading offsets against the best cost found so far;
@@ -138,6 +140,14 @@ MPCB_API int mpcb_solve_batch_device(mpcb_handle *h, int mode, int cost_kind, in
                             const double *threshold, const uint8_t *flags,
                             int64_t i0_begin, int64_t i0_end,
                             double *best_cost, int64_t *best_index, double *best_traj, double *first_control);
+
+/* One online tick in ONE call: mpcb_set_grid(v, beta, ...) followed by a single HELD solve -- what
+ * math_model_tree.predictive_control does per tick with the window lists handed to it (math_model_tree.py:543-551).
+ * Host pointers; threshold = +inf accepts every leaf; flags = MPCB_FLAG_*. */
+MPCB_API int mpcb_held_tick_host(mpcb_handle *h, const double *v, int nv, const double *beta, int nb,
+                        double L, double delta_t, double v_min, int cost_kind, int H,
+                        const double *state, const double *target, const double *origin, double threshold, int flags,
+                        double *best_cost, int64_t *best_index, double *best_traj, double *first_control);
 
 /* Every leaf of ONE small tree in enumeration order (debug / plots / parity): the
  * reference scatters all leaf positions (math_model.py:192-193,204).
@@ -238,8 +248,10 @@ MPCB_API int mpcb_full_closed_loop_host(mpcb_handle *h, int cost_kind, int H, in
 
 /* ONE oversized FULL tree per solve, shared by the ranks of an NCCL communicator (one process per GPU): rank r of R
  * expands the first controls of its contiguous, balanced share of [0, S) -- so rank order is leaf-index order --
- * and reduces it to a (float64 cost, int64 index) record per solve; ONE collective, an ncclAllGather of those 16-byte
- * records over NVLink, gives every rank all R of them; a local kernel takes their lexicographic minimum and every
+ * and reduces it to a (float64 cost, int64 index) record per solve; ONE collective on the data path, an ncclAllGather
+ * of those 16-byte records over NVLink, gives every rank all R of them (with the branch-and-bound or the screened
+ * pass 1 a second 8-byte all-gather shares the ranks' initial upper bounds before the descent, so that a rank whose
+ * share holds no good leaf still prunes against the best bound known); a local kernel takes their lexicographic minimum and every
  * rank re-rolls the winner's trajectory itself (no broadcast).  The only coupling between the leaves of the
  * reference's tree is the running strict-'<' minimum (math_model.py:195-198); this is its multi-GPU form.
  * Collective call: every rank of the communicator must make it with the same arguments (N solves, same states);

