@@ -1,6 +1,9 @@
 """Lists the loops of one kernel's SASS (cuobjdump -sass -fun NAME lib.so) with their instruction mix.
 
-    python tools/sass_loops.py lib.so MANGLED_NAME [min_instructions]
+    python tools/sass_loops.py lib.so MANGLED_NAME [min_instructions] [--dump OP:N]
+
+--dump OP:N prints the body of the innermost loops that hold exactly N instructions with mnemonic OP
+(e.g. FFMA2:128 = the unrolled screen loop of prefixn_kernel).
 
 A loop = the address range of a backward branch [target, branch]; only the innermost ranges are of interest.
 """
@@ -12,7 +15,11 @@ import sys
 
 def main():
     lib, fun = sys.argv[1], sys.argv[2]
-    min_ins = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    min_ins = int(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else 16
+    dump = None
+    if "--dump" in sys.argv:
+        op, n = sys.argv[sys.argv.index("--dump") + 1].split(":")
+        dump = (op, int(n))
     txt = subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], capture_output=True, text=True).stdout
     ins = []
     for line in txt.splitlines():
@@ -38,6 +45,10 @@ def main():
             ops[t.split()[0]] += 1
         top = ", ".join(f"{k} {v}" for k, v in ops.most_common(14))
         print(f"  loop {ins[lo][0]:#06x}..{ins[hi][0]:#06x} ({hi - lo + 1} instr{', has inner loops' if inner else ''}): {top}")
+        if dump and not inner and ops.get(dump[0]) == dump[1]:
+            for a_, t_ in ins[lo:hi + 1]:
+                print(f"      /*{a_:04x}*/  {t_}")
+            dump = None                      # the first match only
 
 
 if __name__ == "__main__":
