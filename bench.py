@@ -47,16 +47,17 @@ SM_COUNT = 148
 MUFU_PER_CLK_SM = 16       # XU lanes per SM per clock
 FP32_PER_CLK_SM = 128
 
-# What the pass-1 kernels execute per rollout, counted in the SASS of their inner loops (profiles/r2_sass_loops.txt;
-# tools/sass_loops.py prints them from the built library).  fp32 = FP32-pipe lane slots (an FFMA2 / FADD2 is two),
-# mufu = XU operations, instr = all warp instructions x 1/32.
+# What the pass-1 kernels execute per rollout: FP32-pipe lane slots (an FFMA2 / FADD2 is two) and XU operations counted
+# in the SASS of their inner loops (profiles/r2_sass_loops.txt; tools/sass_loops.py prints them from the built library),
+# instr = warp instructions x 32 / rollouts of the whole kernel as ncu counts them (smsp__inst_executed.sum,
+# profiles/r2j_cfg2_full.txt, r2j_leafwalk_full.txt, r1l_cfg2_full.txt).
 EXECUTED = {
-    # screen loop of prefixn_kernel<.,2,1>: per node and leaf PAIR 8 FFMA2 + 1 FADD2 + 1 FMNMX3 + 1 LDS.128
-    "prefix_screen": dict(kernel="prefixn_kernel<true,2,1> (pass 1, screen loop)", fp32=9.0, mufu=0.0, instr=5.6, bound="fp32"),
-    # full loop of prefixn_kernel<.,2,0>: per node and leaf pair 7 FFMA2 + 1 FADD2 + 2 MUFU.SQRT + 1 FMNMX3 + 1 LDS.128
-    "prefix_full": dict(kernel="prefixn_kernel<true,2,0> (pass 1)", fp32=8.0, mufu=1.0, instr=6.1, bound="fp32+xu"),
-    # leafwalk_kernel<1,true,1>, H=3: 7 MUFU (sin, cos per step + one sqrt) of 64 executed instructions (ncu, r1y)
-    "leafwalk": dict(kernel="leafwalk_kernel<1,true,1> (pass 1)", fp32=24.0, mufu=7.0, instr=64.0, bound="xu"),
+    # screen loop of prefixn_kernel<.,2,true>: per node and leaf PAIR 8 FFMA2 + 1 FADD2 + 1 FMNMX3 + 1 LDS.128, no MUFU
+    "prefix_screen": dict(kernel="prefixn_kernel<true,2,true> (pass 1, screen loop)", fp32=9.0, mufu=0.0, instr=6.52),
+    # full loop of prefixn_kernel<.,2,false>: per node and leaf pair 7 FFMA2 + 1 FADD2 + 2 MUFU.SQRT + 1 FMNMX3 + 1 LDS.128
+    "prefix_full": dict(kernel="prefixn_kernel<true,2,false> (pass 1)", fp32=8.0, mufu=1.0, instr=6.95),
+    # leafwalk_kernel<1,true,1>, H=3: 7 MUFU (sin + cos per step, one sqrt), 15 scalar FP32 ops, 56.6 instructions in all
+    "leafwalk": dict(kernel="leafwalk_kernel<1,true,1> (pass 1)", fp32=15.0, mufu=7.0, instr=56.6),
 }
 
 
@@ -92,7 +93,7 @@ def peaks():
 def ncu_record(kernel_key):
     """Figures of the committed ncu --set full capture of the dominant kernel (profiles/*_full.txt, newest round first):
     DRAM traffic per launch and the pipe utilisations.  None when no capture of that kernel is committed."""
-    want = {"prefix_screen": r"prefixn_kernel<1, 2, 1>", "prefix_full": r"prefixn_kernel<1, 2(, 0)?>",
+    want = {"prefix_screen": r"prefixn_kernel<1, 2, 1>", "prefix_full": r"prefixn_kernel<1, 2(, 0)?>\(",
             "leafwalk": r"leafwalk_kernel<1, 1, 1>"}[kernel_key]
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_full.txt")), reverse=True):
         try:
@@ -531,8 +532,8 @@ def leg_split_tree(solver, nat, C, torch, dist, dev, ext, world, rank):
 
 def leg_leafwalk(solver, nat, C, torch, dev, ext, wl, scen, pk):
     """The one-thread-per-leaf kernel north_star prescribes (accounting A: 2H+1 MUFU per rollout), same workload on a
-    128-robot slice."""
-    n = 128
+    256-robot slice."""
+    n = 256
     Hh = wl["H"]
     S = len(wl["V"]) * len(wl["B"])
     solver.set_grid(wl["V"], wl["B"], C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])

@@ -30,6 +30,7 @@ cudaError_t launch_frontier_expand(cudaStream_t, const LaunchArgs &, int k, cons
                                    const unsigned *src_count, unsigned long long *dst, unsigned *dst_count,
                                    unsigned *overflow, int sms);
 cudaError_t launch_tilewalk_fallback(cudaStream_t, const LaunchArgs &, unsigned long long all_tiles, int sms);
+cudaError_t launch_cand_resolve(cudaStream_t, const LaunchArgs &, int sms);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
@@ -257,7 +258,7 @@ int mpcb_destroy(mpcb_handle *h) {
                       &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
                       &h->loop_status, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
-                      &h->fl_count, &h->nccl_scratch})
+                      &h->fl_count, &h->nccl_scratch, &h->cand, &h->cand_J, &h->cand_sel})
         b->release();
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -283,6 +284,10 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "refine")) h->refine = value != 0.0;
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "zero_copy")) h->zero_copy = value != 0.0;
+    else if (!strcmp(name, "candidate_list")) {
+        if (!(value >= 0.0 && value <= (double)(1u << 26))) return fail(h, MPCB_ERR_INVALID, "candidate_list out of range [0, 2^26]");
+        h->cand_cap = (unsigned)value;
+    }
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
     else if (!strcmp(name, "screen")) h->screen = value != 0.0;
@@ -377,10 +382,18 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     CK(h->lock.ensure(sizeof(int) * N));
     CK(h->ub.ensure(sizeof(unsigned long long) * N));
     // misc: [0..3] work_count (u32) | [8..11] tile_count (u32, subtree cut) | [16..47] counters (4 x u64) |
-    //       [48..55] frontier counts (2 x u32) | [56..59] frontier overflow flag (u32)
+    //       [48..55] frontier counts (2 x u32) | [56..59] frontier overflow flag (u32) | [60..63] candidate count (u32)
     unsigned *work_count = h->misc.as<unsigned>();
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
     CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
+    // candidate list of the refinement: [cand_cap] candidates + their float64 costs, per-solve key and index (all ones)
+    const unsigned cand_cap = h->cand_cap;
+    if (cand_cap) {
+        CK(h->cand.ensure(sizeof(Candidate) * cand_cap));
+        CK(h->cand_J.ensure(sizeof(double) * cand_cap));
+        CK(h->cand_sel.ensure(2 * sizeof(unsigned long long) * N));
+        CK(cudaMemsetAsync(h->cand_sel.p, 0xFF, 2 * sizeof(unsigned long long) * N, h->stream));
+    }
     CK(cudaMemsetAsync(h->segmin.p, 0xFF, sizeof(double) * std::max<unsigned long long>(a.total_segs, 1), h->stream));
 
     a.sp = h->sp.as<SolveParams>();
@@ -393,6 +406,11 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     a.counters = counters;
     a.tau = h->tau.as<double>();
     a.ub = h->ub.as<unsigned long long>();
+    if (cand_cap) {
+        a.cand = h->cand.as<Candidate>(); a.cand_count = h->misc.as<unsigned>() + 15; a.cand_cap = cand_cap;
+        a.cand_J = h->cand_J.as<double>();
+        a.cand_key = h->cand_sel.as<unsigned long long>(); a.cand_idx = a.cand_key + N;
+    }
     a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
     a.npt = h->npt;
     a.screen = (pl.prefix && !a.prune && H >= 2 && h->npt >= 2) ? h->screen : 0;
@@ -472,6 +490,7 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     }
     if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 2, pl.prefix, h->sms)); ++launches;
+        if (a.cand) { CK(launch_cand_resolve(h->stream, a, h->sms)); launches += 3; }
     }
     if (split_comm) {
         CK(h->nccl_scratch.ensure(sizeof(SplitRec) * (size_t)N * (nranks + 1)));

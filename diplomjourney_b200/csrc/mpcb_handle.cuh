@@ -56,6 +56,8 @@ struct mpcb_handle_s {
     // scratch
     mpcb::DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list, reduce_scratch;
     mpcb::DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
+    mpcb::DevBuf cand, cand_J, cand_sel;  // refinement: listed candidates, their float64 costs, per-solve (key, index)
+    unsigned cand_cap = 1u << 20;       // entries of that list (option "candidate_list"; 0 = evaluate where found)
     mpcb::DevBuf nccl_scratch;          // split tree: this rank's (cost, index) records + one slot per rank
     mpcb::DevBuf loop_log, loop_ticks, loop_status, small_in, small_out, fl_last, fl_k, fl_have, fl_flags, fl_count;
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path

@@ -241,10 +241,24 @@ __device__ __noinline__ double exact_child_cost(const LaunchArgs &a, const Solve
     return exact_terminal(a, P, x, y, phi);
 }
 
-// candidate found by the refinement filter: evaluate and fold into the thread's running best
-__device__ __forceinline__ void take_candidate(const LaunchArgs &a, const SolveParams &P, long long j,
+// candidate found by the refinement filter: listed for cand_eval_kernel (float64 evaluation, one thread per candidate:
+// the in-window leaves of a solve cluster in a few nodes, and a thread evaluating its node's candidates one after the
+// other -- three double-precision sincos each -- was most of pass 2); true = listed
+__device__ __forceinline__ bool cand_push(const LaunchArgs &a, long long n, long long j, double jrel) {
+    if (!a.cand) return false;
+    const unsigned slot = atomicAdd(a.cand_count, 1u);
+    if (slot >= a.cand_cap) return false;                  // list full: the caller evaluates it where it stands
+    Candidate c;
+    c.j = j; c.jrel = jrel; c.n = (int)n; c.pad = 0;
+    a.cand[slot] = c;
+    return true;
+}
+
+// ... or, when the list is full, evaluated on the spot and folded into the thread's running best
+__device__ __forceinline__ void take_candidate(const LaunchArgs &a, const SolveParams &P, long long n, long long j,
                                                double jrel32, double &bJ, long long &bj) {
     atomicAdd(a.counters + 1, 1ULL);
+    if (cand_push(a, n, j, jrel32)) return;
     double J = a.refine ? exact_cost(a, P, j, nullptr, nullptr) : (P.Kbase + jrel32);
     lex_min(bJ, bj, J, j);
 }
@@ -340,6 +354,29 @@ __device__ __forceinline__ float prefix_min_loop_far2(const float4 *__restrict__
         const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
         const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
         // leaf_val_direct on two leaves at a time
+        const float2 dd = __ffma2_rn(U2, A, __ffma2_rn(W2, B, __ffma2_rn(K2, R, D2)));
+        const float2 q = __ffma2_rn(NU, A, __ffma2_rn(NW, B, EH));
+        float2 acc = __ffma2_rn(q, q, make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)));
+        if (HEAD) { const float2 gg = __fadd2_rn(G, NHH); acc = __ffma2_rn(gg, gg, acc); }
+        best = fminf(best, fminf(acc.x, acc.y));
+    }
+    return best;
+}
+
+// The same loop for ONE node shared by the warp (pruned pass 1, sparse survivors): lane l scores leaf pairs l, l + 32,
+// ...; the caller reduces over the lanes.  Per leaf the arithmetic is that of prefix_min_loop_far2 and the minimum does
+// not depend on the order it is taken in, so the node's value is bit-identical.
+template <bool HEAD>
+__device__ __forceinline__ float prefix_min_loop_far2_lanes(const float4 *__restrict__ tab, int npairs, float u2s, float w2s,
+                                                            float D2s, float nu, float nw, float eh, float nhh, int lane) {
+    const float2 U2 = make_float2(u2s, u2s), W2 = make_float2(w2s, w2s), D2 = make_float2(D2s, D2s);
+    const float2 K2 = make_float2(kWd2f, kWd2f), NU = make_float2(nu, nu), NW = make_float2(nw, nw);
+    const float2 EH = make_float2(eh, eh), NHH = make_float2(nhh, nhh);
+    float best = INFINITY;
+    for (int m = lane; m < npairs; m += 32) {
+        const float4 t0 = tab[2 * m], t1 = tab[2 * m + 1];
+        const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
+        const float2 R = make_float2(t1.x, t1.y), G = make_float2(t1.z, t1.w);
         const float2 dd = __ffma2_rn(U2, A, __ffma2_rn(W2, B, __ffma2_rn(K2, R, D2)));
         const float2 q = __ffma2_rn(NU, A, __ffma2_rn(NW, B, EH));
         float2 acc = __ffma2_rn(q, q, make_float2(sqrt_approx(dd.x), sqrt_approx(dd.y)));
@@ -450,7 +487,9 @@ __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict
 // window are skipped lane by lane (a queue that compacts the survivors across tiles was measured 1.3-4x SLOWER:
 // it serialises the float64 set-up and the fp32 pair loop that otherwise overlap between warps).
 template <int PASS, bool HEAD, bool PRUNE = false, bool QMODE = false>
-__global__ void __launch_bounds__((PASS == 1 && !PRUNE) ? kPrefixCta : kThreads, (PASS == 1 && PRUNE) ? 4 : 1)
+// (pass 2 walks a short work list of tiles, each a chain of float64 set-up, filter and publication: it is latency-bound,
+//  so it runs at four CTAs per SM -- 64 registers -- rather than at the two its natural 116 registers allow)
+__global__ void __launch_bounds__((PASS == 1 && !PRUNE) ? kPrefixCta : kThreads, (PASS == 1 && !PRUNE) ? 1 : 4)
 prefix_kernel(const LaunchArgs a) {
     extern __shared__ float4 s_leaf[];
     __shared__ double s_J[kThreads / 32];
@@ -526,7 +565,7 @@ prefix_kernel(const LaunchArgs a) {
             double base = 0.0, base_direct = 0.0, lb = -INFINITY;
             bool active = in_range;
             if (active) base = parent_setup(a, P, p, pr, near, unmoved, &lb, PASS == 1 ? &base_direct : nullptr);
-            if (PASS == 2 && a.prune && active && lb > tau + P.tol) active = false;   // cannot hold an in-window leaf
+            if (PASS == 2 && active && lb > tau + P.tol) active = false;   // no child can lie inside the window
             if (PASS == 1 && PRUNE) {
                 const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
                 const bool cut = active && lb > bound;
@@ -550,31 +589,66 @@ prefix_kernel(const LaunchArgs a) {
                     for (int i = tid; i < chunk_f4(cn); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
                     __syncthreads();
                 }
+                if (PASS == 1 && PRUNE) {
+                    // After the cut the survivors are a few scattered lanes per warp (the promising nodes are a few steering
+                    // directions per speed).  A lane running the pair loop on its own keeps the other 31 idle for S/2
+                    // iterations, so sparse survivors are scored by the WHOLE warp instead, one node at a time with its
+                    // leaf pairs spread over the lanes; dense warps keep one node per lane.
+                    const int npairs = (cn + 1) >> 1;
+                    const bool far_node = active && !(near || special);
+                    unsigned coop = __ballot_sync(0xffffffffu, far_node);
+                    if (__popc(coop) > 12) coop = 0;
+                    const int lane = tid & 31;
+                    for (unsigned todo = coop; todo; todo &= todo - 1) {
+                        const int src = __ffs(todo) - 1;
+                        float v = prefix_min_loop_far2_lanes<HEAD>(
+                            s_leaf, npairs, __shfl_sync(0xffffffffu, pr.u2s, src), __shfl_sync(0xffffffffu, pr.w2s, src),
+                            __shfl_sync(0xffffffffu, pr.D2s, src), __shfl_sync(0xffffffffu, pr.nu, src),
+                            __shfl_sync(0xffffffffu, pr.nw, src), __shfl_sync(0xffffffffu, pr.eh, src),
+                            __shfl_sync(0xffffffffu, pr.nhh, src), lane);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                        if (lane == src) best = fminf(best, v);
+                    }
+                    if (active && !((coop >> lane) & 1u))
+                        best = (near || special) ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr, near, special, Lspecial, best)
+                                                 : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr, best);
+                    continue;
+                }
+                if (PASS == 2) {
+                    // Refinement filter: of a listed tile's 256 nodes only the few whose bound reaches into the window are
+                    // still active, so -- as in the pruned pass 1 -- the warp takes them one at a time with the node's S
+                    // leaves spread over its lanes (a lane scanning its node alone kept the other 31 idle for S iterations).
+                    const int lane = tid & 31;
+                    for (unsigned todo = __ballot_sync(0xffffffffu, active); todo; todo &= todo - 1) {
+                        const int src = __ffs(todo) - 1;
+                        ParentRegs q;
+                        q.u = __shfl_sync(0xffffffffu, pr.u, src); q.w = __shfl_sync(0xffffffffu, pr.w, src);
+                        q.u2 = __shfl_sync(0xffffffffu, pr.u2, src); q.w2 = __shfl_sync(0xffffffffu, pr.w2, src);
+                        q.D2 = __shfl_sync(0xffffffffu, pr.D2, src); q.Dp = __shfl_sync(0xffffffffu, pr.Dp, src);
+                        q.nu = __shfl_sync(0xffffffffu, pr.nu, src); q.nw = __shfl_sync(0xffffffffu, pr.nw, src);
+                        q.e2 = __shfl_sync(0xffffffffu, pr.e2, src); q.h2 = __shfl_sync(0xffffffffu, pr.h2, src);
+                        const bool qnear = __shfl_sync(0xffffffffu, (int)near, src) != 0;
+                        const bool qspecial = __shfl_sync(0xffffffffu, (int)special, src) != 0;
+                        const float qLsp = __shfl_sync(0xffffffffu, Lspecial, src), qthr = __shfl_sync(0xffffffffu, thr, src);
+                        const double qbase = __shfl_sync(0xffffffffu, base, src);
+                        const unsigned long long qp = __shfl_sync(0xffffffffu, p, src);
+                        for (int c = lane; c < cn; c += 32) {
+                            const float4 t = s_leaf[c];
+                            float L = qnear ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, q)
+                                            : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, q);
+                            if (qspecial && t.z == 0.f) L = qLsp;
+                            if (L <= qthr)      // in-window leaf: listed for the float64 evaluation, or evaluated here if the list is full
+                                take_candidate(a, P, n, (long long)(qp * (unsigned long long)S + c0 + c), qbase + (double)L, bJ, bj);
+                        }
+                    }
+                    continue;
+                }
                 if (!active) continue;
-                if (PASS == 1) {
+                {
                     const int npairs = (cn + 1) >> 1;
                     best = (near || special) ? prefix_min_loop_scalar<HEAD>(s_leaf, npairs, pr, near, special, Lspecial, best)
                                              : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr, best);
-                } else {
-                    for (int c = 0; c < cn; ++c) {
-                        float4 t = s_leaf[c];
-                        float L = near ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, pr)
-                                       : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, pr);
-                        if (special && t.z == 0.f) L = Lspecial;
-                        if (L <= thr) {
-                            // in-window leaf: float64 re-evaluation; the node's exact pose is walked once
-                            const long long j = (long long)(p * (unsigned long long)S + c0 + c);
-                            atomicAdd(a.counters + 1, 1ULL);
-                            double J;
-                            if (a.refine) {
-                                if (!have_pose) { exact_prefix(a, P, p, ex, ey, ephi); have_pose = true; }
-                                J = exact_child_cost(a, P, ex, ey, ephi, (unsigned)(c0 + c));
-                            } else {
-                                J = P.Kbase + (base + (double)L);
-                            }
-                            lex_min(bJ, bj, J, j);
-                        }
-                    }
                 }
             }
             if (PASS == 1 && active) segbest = fmin(segbest, base + (double)best);
@@ -1176,7 +1250,7 @@ __device__ __forceinline__ void leafwalk_body(const LaunchArgs &a, const float2 
                     const float L = smem ? leafwalk_eval<HEAD, KIND, true, HT, PASS == 1>(a, P, pr, ctl, j, xi, eta, psi, Lsp)
                                          : leafwalk_eval<HEAD, KIND, false, HT, PASS == 1>(a, P, pr, ctl, j, xi, eta, psi, Lsp);
                     if (PASS == 1) best = fminf(best, L);
-                    else if (L <= thr) take_candidate(a, P, (long long)j, base + (double)L, bJ, bj);
+                    else if (L <= thr) take_candidate(a, P, n, (long long)j, base + (double)L, bJ, bj);
                 }
             }
         }
@@ -1444,6 +1518,37 @@ __global__ void __launch_bounds__(kThreads) seg_compact_kernel(const LaunchArgs 
     }
 }
 
+// Refinement, second half: every listed candidate is evaluated in float64 by its own thread (reference formula and
+// operation order, exact_cost), the smallest cost per solve is folded with an atomicMin on its order-preserving key ...
+__global__ void __launch_bounds__(kThreads) cand_eval_kernel(const LaunchArgs a) {
+    const unsigned count = min(*a.cand_count, a.cand_cap);
+    for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < count; i += gridDim.x * kThreads) {
+        const Candidate c = a.cand[i];
+        const double J = a.refine ? exact_cost(a, a.sp[c.n], c.j, nullptr, nullptr) : (a.sp[c.n].Kbase + c.jrel);
+        a.cand_J[i] = J;
+        if (J == J) atomicMin(a.cand_key + c.n, ordered_key(J));         // NaN costs never win
+    }
+}
+
+// ... then the lowest leaf index among the candidates of that cost (first minimum, math_model.py:195) ...
+__global__ void __launch_bounds__(kThreads) cand_select_kernel(const LaunchArgs a) {
+    const unsigned count = min(*a.cand_count, a.cand_cap);
+    for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < count; i += gridDim.x * kThreads) {
+        const Candidate c = a.cand[i];
+        const double J = a.cand_J[i];
+        if (J == J && ordered_key(J) == a.cand_key[c.n]) atomicMin(a.cand_idx + c.n, (unsigned long long)c.j);
+    }
+}
+
+// ... and merged with what pass 2 evaluated on the spot (only when the list overflowed): the solve's record.
+__global__ void cand_merge_kernel(const LaunchArgs a) {
+    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (n >= a.N) return;
+    double J = a.bestJ[n]; long long j = a.bestIdx[n];
+    if (a.cand_key[n] != ~0ULL) lex_min(J, j, ordered_value(a.cand_key[n]), (long long)a.cand_idx[n]);
+    a.bestJ[n] = J; a.bestIdx[n] = j;
+}
+
 // Winner -> outputs: float64 re-roll of its trajectory, threshold test (math_model.py:195).
 __global__ void finalize_kernel(const LaunchArgs a, double *best_cost, long long *best_index, double *best_traj,
                                 double *first_control) {
@@ -1651,6 +1756,13 @@ cudaError_t launch_reduce_compact_wide(cudaStream_t st, const LaunchArgs &a, dou
     window_edge_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a, solve_key, tau, tau1);
     seg_compact_kernel<<<grid, kThreads, 0, st>>>(a, tau1, worklist, work_count);
     *launches += 3;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cand_resolve(cudaStream_t st, const LaunchArgs &a, int sms) {
+    cand_eval_kernel<<<sms * 4, kThreads, 0, st>>>(a);
+    cand_select_kernel<<<sms * 4, kThreads, 0, st>>>(a);
+    cand_merge_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -125,6 +125,10 @@ struct __align__(16) SolveParams {
 };
 constexpr int kFlagSlow = 1, kFlagStartIsOrigin = 2, kFlagNear = 4, kFlagSkip = 8;
 
+// refinement: a leaf whose fp32 value lies inside the window, waiting for its float64 evaluation (pass 2 lists them,
+// cand_eval_kernel evaluates them one thread each)
+struct __align__(8) Candidate { long long j; double jrel; int n; int pad; };
+
 struct LaunchArgs {
     GridTables g;
     const SolveParams *sp;
@@ -166,6 +170,11 @@ struct LaunchArgs {
     int npt;                               // depth-(H-1) nodes per thread in the exhaustive prefix pass 1 (1 or 2)
     int i0_begin, i0_end;                   // first-control range of this launch (probe)
     const double *tau;                     // [N] J_rel window upper edge
+    // candidate list of the refinement (null: every candidate is evaluated where it is found)
+    Candidate *cand; unsigned *cand_count; unsigned cand_cap;
+    double *cand_J;                        // [cand_cap] float64 cost of each listed candidate
+    unsigned long long *cand_key;          // [N] ordered key of the smallest listed cost per solve
+    unsigned long long *cand_idx;          // [N] smallest leaf index among the listed candidates of that cost
     // dump
     float4 *dump;                          // {x, y, phi, J_rel} per leaf
     unsigned long long dump_begin, dump_count;

@@ -109,6 +109,9 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * of the node may have and still beat the solve's upper bound (an exact probe of the S held sequences, tightened by
  * every node that found something), a leaf matters iff t = cn - q^2 - gg^2 > 0 and fma(t, t, -dd) > 0; such nodes are
  * re-run with the square roots.  0: one MUFU.SQRT per leaf, no upper bound involved),
+ * "candidate_list" (entries, default 2^20; identical results: the refinement pass lists the leaves whose fp32 value lies
+ * inside the error window and a second kernel evaluates them in float64 one thread each; candidates beyond the capacity
+ * -- or all of them with 0 -- are evaluated by the thread that found them),
  * "nodes_per_thread" (1, 2 or 4, default 2: depth-(H-1) nodes each thread of the exhaustive prefix pass 1 holds --
  * identical results), "dump_direct" (diagnostics: mpcb_dump_leaves_host returns the cheaper fp32 form pass 1 ranks
  * with instead of the one pass 2 filters with; default 0), "frontier_cap" (see "subtree_cut"). */

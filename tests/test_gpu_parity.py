@@ -70,7 +70,7 @@ def test_held_golden_reference_outputs(solver, golden, small_path):
         ret = list(r["traj"][0, 0]) + list(r["first_control"][0])
         np.testing.assert_allclose(ret, c["ret"], rtol=0, atol=1e-12)
         np.testing.assert_allclose(r["traj"][0], np.array(c["traj"]), rtol=0, atol=1e-12)
-        assert solver.stats()["kernel_launches"] == (1 if small_path else 5)
+        assert solver.stats()["kernel_launches"] == (1 if small_path else 8)   # prep, pass 1, reduce, pass 2, 3 x candidates, finalize
     solver.set_option("small_path", 1)
 
 
@@ -523,5 +523,34 @@ def test_screened_pass1_is_exact(solver, cost):
                         assert res[1]["index"][i] == o["index"], (S, H, i)
     finally:
         solver.set_option("screen", 1)
+        solver.set_option("prune", 1)
+        solver.set_option("algo", nat.ALGO_AUTO)
+
+
+@pytest.mark.parametrize("algo", [nat.ALGO_LEAFWALK, nat.ALGO_PREFIX])
+def test_candidate_list_sizes_give_identical_records(solver, algo):
+    """option candidate_list: the in-window leaves of the refinement pass are listed and evaluated in float64 one thread
+    each; with a list that is too small (5 entries) the excess -- and with 0 every one -- is evaluated by the thread that
+    found it.  Same records in every case, also with many exact ties (zero-velocity leaves) and under pruning."""
+    V, B = np.linspace(0.0, 1.0, 9), np.linspace(-1.0, 1.0, 11)
+    solver.set_grid(V, B, L, DT, VMIN)
+    sc = C.random_scenarios(12, 77)
+    sc[1, 3:5] = sc[1, :2] + [0.0, 1e-3]                        # the optimum stands still: thousands of tied candidates
+    solver.set_option("algo", algo)
+    try:
+        for prune in (0, 1):
+            solver.set_option("prune", prune)
+            res = []
+            for cap in (1 << 20, 5, 0):
+                solver.set_option("candidate_list", cap)
+                res.append(solver.solve(nat.MODE_FULL, nat.COST_MM, 3, sc[:, :3], sc[:, 3:5], sc[:, :2]))
+                assert solver.stats()["refine_candidates"] >= len(sc)
+            for r in res[1:]:
+                for k in ("index", "cost", "traj", "first_control"):
+                    np.testing.assert_array_equal(r[k], res[0][k])
+            for i, s_ in enumerate(sc):
+                _check(res[0], i, K.solve_full(s_[:3], s_[3:], s_[:2], V, B, 3, C.COST_MM), 3)
+    finally:
+        solver.set_option("candidate_list", 1 << 20)
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
