@@ -531,9 +531,9 @@ def leg_split_tree(solver, nat, C, torch, dist, dev, ext, world, rank):
 
 
 def leg_leafwalk(solver, nat, C, torch, dev, ext, wl, scen, pk):
-    """The one-thread-per-leaf kernel north_star prescribes (accounting A: 2H+1 MUFU per rollout), same workload on a
-    256-robot slice."""
-    n = 256
+    """The one-thread-per-leaf kernel north_star prescribes (accounting A: 2H+1 MUFU per rollout), same workload (all
+    robots: the persistent grid needs a few hundred ms of work per launch to hide its tail)."""
+    n = len(scen)
     Hh = wl["H"]
     S = len(wl["V"]) * len(wl["B"])
     solver.set_grid(wl["V"], wl["B"], C.CONFIG["L"], C.CONFIG["delta_t"], C.CONFIG["v_min"])
@@ -552,7 +552,7 @@ def leg_leafwalk(solver, nat, C, torch, dev, ext, wl, scen, pk):
         step()
     solver.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 4
+    reps = 3
     with torch.cuda.stream(ext):
         e0.record()
         for _ in range(reps):
