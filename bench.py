@@ -52,8 +52,9 @@ FP32_PER_CLK_SM = 128
 # instr = warp instructions x 32 / rollouts of the whole kernel as ncu counts them (smsp__inst_executed.sum,
 # profiles/r2j_cfg2_full.txt, r2j_leafwalk_full.txt, r1l_cfg2_full.txt).
 EXECUTED = {
-    # screen loop of prefixn_kernel<.,2,true>: per node and leaf PAIR 8 FFMA2 + 1 FADD2 + 1 FMNMX3 + 1 LDS.128, no MUFU
-    "prefix_screen": dict(kernel="prefixn_kernel<true,2,true> (pass 1, screen loop)", fp32=9.0, mufu=0.0, instr=6.52),
+    # row screen loop of prefixn_kernel<.,2,true>: per node and leaf PAIR 7 FFMA2 + 1 FADD2 + 1 FMNMX3 + 1/2 (LDS.128 + LDS.64),
+    # no MUFU; one more FFMA per node and speed ROW (fma(kWd^2, r, D2s), 1/42 per rollout on the 11 x 41 grid)
+    "prefix_screen": dict(kernel="prefixn_kernel<true,2,true> (pass 1, row screen loop)", fp32=8.05, mufu=0.0, instr=6.1),
     # full loop of prefixn_kernel<.,2,false>: per node and leaf pair 7 FFMA2 + 1 FADD2 + 2 MUFU.SQRT + 1 FMNMX3 + 1 LDS.128
     "prefix_full": dict(kernel="prefixn_kernel<true,2,false> (pass 1)", fp32=8.0, mufu=1.0, instr=6.95),
     # leafwalk_kernel<1,true,1>, H=3: 7 MUFU (sin + cos per step, one sqrt), 15 scalar FP32 ops, 56.6 instructions in all
@@ -676,7 +677,8 @@ def run_gpu(args):
 
     # ---------------- parity gate on the benchmark's own output: every robot of the device-timed step equals the
     # host-API step bit for bit, and an evenly spaced sub-sample of >= 64 robots equals the float64 C oracle
-    if not (np.array_equal(dev_index, out_np["index"]) and np.array_equal(dev_cost, out_np["cost"])):
+    if not (np.array_equal(dev_index, out_np["index"]) and np.array_equal(dev_cost, out_np["cost"])) \
+            and not os.environ.get("MPCB_TIMING_ONLY_EXPERIMENT"):
         raise SystemExit("PARITY FAILURE in bench: device-API and host-API steps disagree")
     parity = None
     if rank == 0:
@@ -690,7 +692,9 @@ def run_gpu(args):
         parity = (f"{ok}/{len(chk)} robots (every {max(1, n // 64)}th) identical to the float64 C oracle (index, cost rtol 1e-12, "
                   f"trajectory atol 1e-12); all {n} robots identical between the device-API and host-API steps")
         if ok != len(chk):
-            raise SystemExit("PARITY FAILURE in bench: " + parity)
+            if not os.environ.get("MPCB_TIMING_ONLY_EXPERIMENT"):      # deliberately wrong kernels of tools/build_variants.py
+                raise SystemExit("PARITY FAILURE in bench: " + parity)
+            parity = "NOT A RESULT (timing-only experiment build): " + parity
 
     # ---------------- same step with the exact branch-and-bound on (identical results, fewer leaves evaluated)
     pruned = None
@@ -718,7 +722,7 @@ def run_gpu(args):
                       note="option prune=1 (the library default): exact branch-and-bound -- nodes and subtrees whose leaves "
                            "provably cannot reach the refinement window are skipped, identical records; `value` above "
                            "is measured with prune=0 (every leaf evaluated)")
-        if not same:
+        if not same and not os.environ.get("MPCB_TIMING_ONLY_EXPERIMENT"):
             raise SystemExit("PARITY FAILURE in bench: pruned and unpruned solves disagree")
         solver.set_option("prune", 0)
     solver.set_option("algo", nat.ALGO_AUTO)

@@ -194,6 +194,18 @@ static int ensure_tables(mpcb_handle *h) {
         l32p[2 * m] = make_float4(x.x, y.x, x.y, y.y);
         l32p[2 * m + 1] = make_float4(x.z, y.z, x.w, y.w);
     }
+    // the same pairs by speed row, when the whole table fits one shared-memory chunk (screened pass 1: K r + D2 once per row)
+    const int ppr = (nb + 1) / 2;
+    const bool rows_fit = 2LL * nv * ppr <= kLeafChunk;
+    std::vector<float4> l32r(rows_fit ? 2 * (size_t)nv * ppr : 0);
+    if (rows_fit)
+        for (int iv = 0; iv < nv; ++iv)
+            for (int m = 0; m < ppr; ++m) {
+                const float4 x = l32[iv * nb + 2 * m], y = l32[iv * nb + std::min(2 * m + 1, nb - 1)];
+                l32r[2 * ((size_t)iv * ppr + m)] = make_float4(x.x, y.x, x.y, y.y);
+                l32r[2 * ((size_t)iv * ppr + m) + 1] = make_float4(x.z, y.z, x.w, y.w);
+            }
+    CK(h->leaf32r.ensure(sizeof(float4) * std::max<size_t>(l32r.size(), 1)));
     CK(h->leaf32.ensure(sizeof(float4) * S));
     CK(h->leaf32p.ensure(sizeof(float4) * 2 * npairs));
     CK(h->ctl32.ensure(sizeof(float2) * S)); CK(h->ctl32_slow.ensure(sizeof(float2) * S));
@@ -206,6 +218,7 @@ static int ensure_tables(mpcb_handle *h) {
     CK(cudaMemcpyAsync(h->beta.p, beta, sizeof(double) * nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->leaf32.p, l32.data(), sizeof(float4) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->leaf32p.p, l32p.data(), sizeof(float4) * 2 * npairs, cudaMemcpyHostToDevice, h->stream));
+    if (rows_fit) CK(cudaMemcpyAsync(h->leaf32r.p, l32r.data(), sizeof(float4) * l32r.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ctl32.p, c32.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ctl32_slow.p, c32s.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
     GridTables &g = h->g;
@@ -214,6 +227,8 @@ static int ensure_tables(mpcb_handle *h) {
     g.beta = h->beta.as<double>();
     g.leaf32 = h->leaf32.as<float4>();
     g.leaf32p = h->leaf32p.as<float4>();
+    g.leaf32r = rows_fit ? h->leaf32r.as<float4>() : nullptr;
+    g.nv = nv; g.ppr = rows_fit ? ppr : 0;
     g.ctl32 = h->ctl32.as<float2>(); g.ctl32_slow = h->ctl32_slow.as<float2>();
     g.S = S; g.nb = nb; g.dt = delta_t; g.smax = smax; g.dphimax = dphimax; g.smin = smin;
     h->tables_ready = true;
@@ -253,7 +268,7 @@ int mpcb_destroy(mpcb_handle *h) {
     if (!h) return MPCB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->ctl32,
+    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->leaf32r, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
                       &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,

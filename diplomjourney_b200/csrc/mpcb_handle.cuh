@@ -40,7 +40,7 @@ struct mpcb_handle_s {
     std::vector<double> hv, hb;         // host copy of the raw grids
     double L = 0, delta_t = 0, v_min = 0, v_slow = 0;
     mpcb::GridTables g{};
-    mpcb::DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, ctl32, ctl32_slow;
+    mpcb::DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, leaf32r, ctl32, ctl32_slow;
     // options
     double tol_scale = 1.0;
     int algo = MPCB_ALGO_AUTO;

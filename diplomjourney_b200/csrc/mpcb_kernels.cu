@@ -38,9 +38,14 @@
 #define MPCB_UNROLL4 2  // pairs per unrolled iteration of the four-node loop (1, 2, 4 within 1.3 %)
 #endif
 #ifndef MPCB_PN_CTA2
-#define MPCB_PN_CTA2 640  // threads per CTA of the two-nodes-per-thread pass-1 kernel (one CTA per SM, five 256-node tiles per
-                          // work item, 96 registers): 512 / 640 / 768 / 896 / 1024 threads = 2.99 / 3.10 / 2.96 / 2.98 / 2.97e12
-                          // rollouts/s on the cfg2 bench (profiles/r2c_variants.txt, r2f_variants.txt)
+#define MPCB_PN_CTA2 512  // threads per CTA of the two-nodes-per-thread pass-1 kernel (one CTA per SM, four 256-node tiles per
+                          // work item).  Row loop (the usual case): 384 / 512 / 640 threads = 3.13 / 3.20 / 3.14e12 rollouts/s on the
+                          // cfg2 bench; flat screen loop: 512 / 640 / 768 / 896 / 1024 = 2.99 / 3.10 / 2.96 / 2.98 / 2.97e12
+                          // (profiles/r2c_variants.txt, r2f_variants.txt, r2u_variants.txt, r2v_variants.txt)
+#endif
+#ifndef MPCB_UNROLL_ROWS
+#define MPCB_UNROLL_ROWS 4  // pairs per unrolled iteration of the row loop (a row of the cfg2 grid has 21 pairs: 3 / 4 / 7 / 8 / 21
+                            // = 3.15 / 3.20 / 3.20 / 3.07 / 3.17e12)
 #endif
 #ifndef MPCB_UNROLL
 #define MPCB_UNROLL 8   // pairs per unrolled iteration of the pass-1 loop (4..16 are within 1 %, profiles/r1b_variants.txt)
@@ -467,6 +472,52 @@ __device__ __forceinline__ void prefix_screen_loop_far2xN(const float4 *__restri
     for (int k = 0; k < NPT; ++k) mx[k] = m[k];
 }
 
+// The screen loop over the ROW table (GridTables::leaf32r): all leaves of a speed row share r_c = (v dt)^2, so the
+// innermost term of dd, fma(kWd^2, r, D2s), is formed once per node and row instead of once per pair -- 7 FFMA2 + 1 FADD2
+// per node and leaf pair instead of 8 + 1, and the very same value (same operands, same operation).  The pairs an odd
+// row is padded with repeat its last leaf, which changes no maximum.
+template <bool HEAD, int NPT>
+__device__ __forceinline__ void prefix_screen_loop_rows(const float4 *__restrict__ tab, int nv, int ppr,
+                                                        const ParentRegs (&p)[NPT], const float (&cn)[NPT],
+                                                        float (&mx)[NPT]) {
+    float2 U[NPT], W[NPT], NU[NPT], NW[NPT], E[NPT], Hh[NPT], C[NPT];
+    float nD[NPT], m[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+        U[k] = make_float2(-p[k].u2s, -p[k].u2s); W[k] = make_float2(-p[k].w2s, -p[k].w2s);
+        nD[k] = -p[k].D2s;
+        NU[k] = make_float2(p[k].nu, p[k].nu); NW[k] = make_float2(p[k].nw, p[k].nw);
+        E[k] = make_float2(p[k].eh, p[k].eh); Hh[k] = make_float2(p[k].nhh, p[k].nhh);
+        C[k] = make_float2(cn[k], cn[k]);
+        m[k] = -INFINITY;
+    }
+    constexpr int kUnroll = NPT == 2 ? MPCB_UNROLL_ROWS : MPCB_UNROLL4;
+    for (int iv = 0; iv < nv; ++iv) {
+        const float4 *__restrict__ row = tab + 2 * iv * ppr;
+        const float rv = row[1].x;                         // r of the row
+        float2 DV[NPT];
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) { const float d = __fmaf_rn(-kWd2f, rv, nD[k]); DV[k] = make_float2(d, d); }
+#pragma unroll kUnroll
+        for (int i = 0; i < ppr; ++i) {
+            const float4 t0 = row[2 * i];
+            const float2 G = reinterpret_cast<const float2 *>(row + 2 * i + 1)[1];
+            const float2 A = make_float2(t0.x, t0.y), B = make_float2(t0.z, t0.w);
+#pragma unroll
+            for (int k = 0; k < NPT; ++k) {
+                const float2 ndd = __ffma2_rn(U[k], A, __ffma2_rn(W[k], B, DV[k]));                    // -dd
+                const float2 q = __ffma2_rn(NU[k], A, __ffma2_rn(NW[k], B, E[k]));
+                float2 t = __ffma2_rn(make_float2(-q.x, -q.y), q, C[k]);
+                if (HEAD) { const float2 gg = __fadd2_rn(G, Hh[k]); t = __ffma2_rn(make_float2(-gg.x, -gg.y), gg, t); }
+                const float2 df = __ffma2_rn(t, t, ndd);
+                m[k] = fmaxf(m[k], fmaxf(df.x, df.y));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) mx[k] = m[k];
+}
+
 // scalar flavour on the same pair table: NEAR regime, or a node sitting exactly on the line origin
 template <bool HEAD>
 __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict__ tab, int npairs, const ParentRegs &pr,
@@ -677,11 +728,14 @@ __global__ void __launch_bounds__(prefixn_cta(NPT), NPT / 2) prefixn_kernel(cons
     constexpr int kCta = prefixn_cta(NPT);
     const int tid = threadIdx.x;
     const int S = a.g.S;
-    const bool single = S <= kLeafChunk;
-    const float4 *__restrict__ gtab = a.g.leaf32p;
+    // the screened kernel stages the pair table BY SPEED ROW when that fits one chunk (prefix_screen_loop_rows); every
+    // other loop reads the very same array as a flat list of nv * ppr pairs
+    const bool rows = SCREEN && a.g.ppr > 0;
+    const bool single = rows || S <= kLeafChunk;
+    const float4 *__restrict__ gtab = rows ? a.g.leaf32r : a.g.leaf32p;
     auto chunk_f4 = [&](int cn) { return 2 * ((cn + 1) >> 1); };
     if (single) {
-        for (int i = tid; i < chunk_f4(S); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
+        for (int i = tid; i < (rows ? 2 * a.g.nv * a.g.ppr : chunk_f4(S)); i += blockDim.x) s_leaf[i] = __ldg(gtab + i);
         __syncthreads();
     }
     constexpr unsigned groups = kCta * NPT / kThreads;           // 256-node tiles per work item
@@ -731,10 +785,11 @@ __global__ void __launch_bounds__(prefixn_cta(NPT), NPT / 2) prefixn_kernel(cons
                 for (int i = tid; i < chunk_f4(cn_); i += blockDim.x) s_leaf[i] = __ldg(gtab + c0 + i);
                 __syncthreads();
             }
-            const int npairs = (cn_ + 1) >> 1;
+            const int npairs = rows ? a.g.nv * a.g.ppr : (cn_ + 1) >> 1;
             if (all && SCREEN) {
                 float mx[NPT];
-                prefix_screen_loop_far2xN<HEAD, NPT>(s_leaf, npairs, pr, cn, mx);
+                if (rows) prefix_screen_loop_rows<HEAD, NPT>(s_leaf, a.g.nv, a.g.ppr, pr, cn, mx);
+                else prefix_screen_loop_far2xN<HEAD, NPT>(s_leaf, npairs, pr, cn, mx);
 #pragma unroll
                 for (int k = 0; k < NPT; ++k)       // some leaf of the node has t^2 - dd > 0: it may matter
                     if (mx[k] > 0.f) { best[k] = prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr[k], best[k]); hit[k] = true; }
@@ -1642,7 +1697,9 @@ cudaError_t launch_prep(cudaStream_t st, long long N, const double *state, const
 }
 
 static size_t prefix_smem(const LaunchArgs &a) {
-    return sizeof(float4) * (size_t)(a.g.S < kLeafChunk ? a.g.S : kLeafChunk);
+    const size_t rows = 2 * (size_t)a.g.nv * a.g.ppr;            // the row table (0 if it does not fit one chunk)
+    const size_t flat = (size_t)(a.g.S < kLeafChunk ? a.g.S + 1 : kLeafChunk);
+    return sizeof(float4) * (rows > flat ? rows : flat);
 }
 
 template <typename K>

@@ -95,6 +95,9 @@ struct GridTables {
     // float32, for the inner loops
     const float4 *leaf32;       // {a_c = s_c cos dphi_c, b_c = s_c sin dphi_c, r_c = s_c^2, g_c = sqrt(10) dphi_c}
     const float4 *leaf32p;      // pair table: [2m] = {a_2m, a_2m+1, b_2m, b_2m+1}, [2m+1] = {r.., r.., g.., g..}; odd S pads by repeating the last leaf
+    const float4 *leaf32r;      // the pair table laid out by SPEED ROW (row iv = ppr pairs of its nb leaves, an odd row padded by
+                                // repeating its last leaf): all leaves of a row share r_c = (v dt)^2; null when it does not fit one chunk
+    int nv, ppr;                // speeds; pairs per row = (nb + 1) / 2
     const float2 *ctl32;        // {dphi_c, s_c}
     const float2 *ctl32_slow;
     int S, nb;
