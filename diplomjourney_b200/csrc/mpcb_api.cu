@@ -183,6 +183,9 @@ static int ensure_tables(mpcb_handle *h) {
                 }
             }
         }
+    std::vector<float4> t32(S);
+    for (int c = 0; c < S; ++c) t32[c] = make_float4((float)t64[c].x, (float)t64[c].y, (float)t64[c].z, (float)t64[c].w);
+    CK(h->tab32.ensure(sizeof(float4) * S));
     CK(h->tab64.ensure(sizeof(double4) * S)); CK(h->tab64_slow.ensure(sizeof(double4) * S));
     CK(h->vtab.ensure(sizeof(double) * S)); CK(h->vtab_slow.ensure(sizeof(double) * S));
     CK(h->beta.ensure(sizeof(double) * nb));
@@ -212,6 +215,7 @@ static int ensure_tables(mpcb_handle *h) {
     // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may die here;
     // ordering against earlier solves on the stream is preserved
     CK(cudaMemcpyAsync(h->tab64.p, t64.data(), sizeof(double4) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tab32.p, t32.data(), sizeof(float4) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->tab64_slow.p, t64s.data(), sizeof(double4) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->vtab.p, vt.data(), sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->vtab_slow.p, vts.data(), sizeof(double) * S, cudaMemcpyHostToDevice, h->stream));
@@ -223,6 +227,7 @@ static int ensure_tables(mpcb_handle *h) {
     CK(cudaMemcpyAsync(h->ctl32_slow.p, c32s.data(), sizeof(float2) * S, cudaMemcpyHostToDevice, h->stream));
     GridTables &g = h->g;
     g.tab64 = h->tab64.as<double4>(); g.vtab = h->vtab.as<double>();
+    g.tab32 = h->tab32.as<float4>();
     g.tab64_slow = h->tab64_slow.as<double4>(); g.vtab_slow = h->vtab_slow.as<double>();
     g.beta = h->beta.as<double>();
     g.leaf32 = h->leaf32.as<float4>();
@@ -268,7 +273,7 @@ int mpcb_destroy(mpcb_handle *h) {
     if (!h) return MPCB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (DevBuf *b : {&h->tab64, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->leaf32r, &h->ctl32,
+    for (DevBuf *b : {&h->tab64, &h->tab32, &h->vtab, &h->tab64_slow, &h->vtab_slow, &h->beta, &h->leaf32, &h->leaf32p, &h->leaf32r, &h->ctl32,
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
                       &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
@@ -306,6 +311,7 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
     else if (!strcmp(name, "screen")) h->screen = value != 0.0;
+    else if (!strcmp(name, "prefilter")) h->prefilter = value != 0.0;
     else if (!strcmp(name, "subtree_cut")) {
         if (value != 0.0 && value != 1.0 && value != 2.0 && value != 3.0) return fail(h, MPCB_ERR_INVALID, "subtree_cut must be 0, 1, 2 or 3");
         h->subtree_cut = (int)value;
@@ -378,6 +384,8 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     fill_args(h, a, mode, cost_kind, H, N, pl);
     const unsigned long long units = pl.u_end - pl.u_begin;
     a.tiles_per_solve = (units + a.tile_units - 1) / a.tile_units;
+    fastdiv_init(a.fd_tiles, std::max<unsigned long long>(a.tiles_per_solve, 1));
+    fastdiv_init(a.fd_S, (unsigned long long)h->g.S);
     unsigned __int128 all_tiles = (unsigned __int128)a.tiles_per_solve * (unsigned long long)N;
     unsigned long long tps = (unsigned long long)((all_tiles + kSegCap - 1) / kSegCap);
     if (tps < 1) tps = 1;
@@ -429,6 +437,7 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
     a.npt = h->npt;
     a.screen = (pl.prefix && !a.prune && H >= 2 && h->npt >= 2) ? h->screen : 0;
+    a.prefilter = h->prefilter;
 
     int launches = 0;
     CK(launch_prep(h->stream, N, state, target, origin, threshold, flags, cost_kind, H, (pl.prefix ? 1 : 0) | (mode == MPCB_MODE_HELD ? 2 : 0),

@@ -10,6 +10,8 @@
 
 namespace mpcb {
 
+using std::fabs; using std::fmin; using std::fmax; using std::sqrt; using std::fma;   // the float overloads too (host build)
+
 // cos / sin of the heading range reachable in i+1 steps, (i+1) dphi_max; cos = -2 marks "the whole circle"
 inline void bounds_set_heading_ranges(LaunchArgs &a, double dphimax) {
     for (int i = 0; i < kMaxH; ++i) {
@@ -19,20 +21,44 @@ inline void bounds_set_heading_ranges(LaunchArgs &a, double dphimax) {
     }
 }
 
-// min over |q| <= Q of q^2 + e q  (the line / heading offset terms of leaf_val are of this form)
-MPCB_HD double quad_min(double e, double Q) {
-    const double ae = fabs(e);
-    return ae <= 2.0 * Q ? -0.25 * e * e : Q * (Q - ae);
+// The scalars the bounds read, in the arithmetic type T they are evaluated in: double for the bounds that decide
+// (every cut is a float64 statement), float for the pre-filter of the pruned pass 1 (node_prefilter32 below).
+template <typename T>
+struct BoundConsts {
+    T smax, smin, dphimax, wl, inv_wl, wh;
+    T cosk[kMaxH], sink[kMaxH];
+};
+
+// (only the heading ranges of the first `steps` steps are filled in: a bound with `steps` steps of slack reads no more)
+template <typename T>
+MPCB_HD BoundConsts<T> bound_consts(const LaunchArgs &a, const SolveParams &P, int steps = kMaxH) {
+    BoundConsts<T> c;
+    c.smax = (T)a.g.smax; c.smin = (T)a.g.smin; c.dphimax = (T)a.g.dphimax;
+    c.wl = (T)P.wl; c.inv_wl = (T)P.inv_wl; c.wh = (T)P.wh;
+    for (int i = 0; i < kMaxH && i < steps; ++i) { c.cosk[i] = (T)a.cosk[i]; c.sink[i] = (T)a.sink[i]; }
+    return c;
 }
 
-// one step of the float64 prefix walk in the start frame: heading by the angle-addition recurrence
-MPCB_HD void walk_step(const double4 t, double &xi, double &eta, double &psi, double &cp, double &sp) {
-    double cn = cp * t.x - sp * t.y;
-    double sn = sp * t.x + cp * t.y;
+// min over |q| <= Q of q^2 + e q  (the line / heading offset terms of leaf_val are of this form)
+template <typename T>
+MPCB_HD T quad_min(T e, T Q) {
+    const T ae = fabs(e);
+    return ae <= T(2) * Q ? T(-0.25) * e * e : Q * (Q - ae);
+}
+
+// one step of the prefix walk in the start frame: heading by the angle-addition recurrence
+// (t = {cos dphi, sin dphi, s, dphi} of the step's control)
+template <typename T>
+MPCB_HD void walk_step_t(T tc, T ts, T tstep, T tdphi, T &xi, T &eta, T &psi, T &cp, T &sp) {
+    const T cn = cp * tc - sp * ts;
+    const T sn = sp * tc + cp * ts;
     cp = cn; sp = sn;
-    xi = fma(t.z, cp, xi);
-    eta = fma(t.z, sp, eta);
-    psi += t.w;
+    xi = fma(tstep, cp, xi);
+    eta = fma(tstep, sp, eta);
+    psi += tdphi;
+}
+MPCB_HD void walk_step(const double4 t, double &xi, double &eta, double &psi, double &cp, double &sp) {
+    walk_step_t<double>(t.x, t.y, t.z, t.w, xi, eta, psi, cp, sp);
 }
 
 // Range [lo, hi] of the displacement of `steps` further control steps along a FIXED direction that makes the angle
@@ -44,22 +70,23 @@ MPCB_HD void walk_step(const double4 t, double &xi, double &eta, double &psi, do
 //    move AWAY from it;
 //  * along the gradient of the signed line distance, wl [lo, hi] brackets the line offset q of every leaf.
 // Grids with negative speeds fall back to the isotropic range +-steps max|s|.
-MPCB_HD void projection_range(const LaunchArgs &a, double cg, double sg, int steps, double &lo,
-                                                 double &hi) {
-    if (a.g.smin < 0.0 || !(cg * cg + sg * sg < 2.0)) { hi = steps * a.g.smax; lo = -hi; return; }   // (NaN: isotropic)
-    lo = 0.0; hi = 0.0;
+template <typename T>
+MPCB_HD void projection_range(const BoundConsts<T> &k, T cg, T sg, int steps, T &lo, T &hi) {
+    if (k.smin < T(0) || !(cg * cg + sg * sg < T(2))) { hi = steps * k.smax; lo = -hi; return; }   // (NaN: isotropic)
+    lo = T(0); hi = T(0);
     for (int i = 0; i < steps; ++i) {
-        const double ci = a.cosk[i], si = a.sink[i];                         // cos, sin of (i+1) dphi_max; -2, 0: whole circle
-        const double cmax = cg >= ci ? 1.0 : cg * ci + sg * si;              // cos(max(0, gamma - (i+1) dphi_max))
-        const double cmin = -cg >= ci ? -1.0 : cg * ci - sg * si;            // cos(min(pi, gamma + (i+1) dphi_max))
-        hi += cmax >= 0.0 ? a.g.smax * cmax : a.g.smin * cmax;
-        lo += cmin <= 0.0 ? a.g.smax * cmin : a.g.smin * cmin;
+        const T ci = k.cosk[i], si = k.sink[i];                          // cos, sin of (i+1) dphi_max; -2, 0: whole circle
+        const T cmax = cg >= ci ? T(1) : cg * ci + sg * si;              // cos(max(0, gamma - (i+1) dphi_max))
+        const T cmin = -cg >= ci ? T(-1) : cg * ci - sg * si;            // cos(min(pi, gamma + (i+1) dphi_max))
+        hi += cmax >= T(0) ? k.smax * cmax : k.smin * cmax;
+        lo += cmin <= T(0) ? k.smax * cmin : k.smin * cmin;
     }
 }
 
 // min over q in [qlo, qhi] of q^2 + e q
-MPCB_HD double quad_min_range(double e, double qlo, double qhi) {
-    const double q = fmin(fmax(-0.5 * e, qlo), qhi);
+template <typename T>
+MPCB_HD T quad_min_range(T e, T qlo, T qhi) {
+    const T q = fmin(fmax(T(-0.5) * e, qlo), qhi);
     return q * (q + e);
 }
 
@@ -67,32 +94,72 @@ MPCB_HD double quad_min_range(double e, double qlo, double qhi) {
 // (ch, sh) is its heading: (rx, ry) target relative to the node and D its length, (nx, ny) gradient of the scaled line
 // distance (length wl), ep scaled line distance, hp scaled heading error -- the closest approach the steering limits
 // allow, the most favourable line offset inside the bracket they allow, the most favourable heading offset.
+template <typename T>
+MPCB_HD T lower_bound_from_t(const BoundConsts<T> &k, T rx, T ry, T D, T nx, T ny, T ch, T sh, T ep, T hp, T base0,
+                             int steps) {
+    T lo, reach, qlo, qhi;
+    if (D > T(0)) {
+        const T inv = T(1) / D;
+        projection_range<T>(k, (rx * ch + ry * sh) * inv, fabs(rx * sh - ry * ch) * inv, steps, lo, reach);
+    } else {
+        reach = steps * k.smax;
+    }
+    projection_range<T>(k, (nx * ch + ny * sh) * k.inv_wl, fabs(nx * sh - ny * ch) * k.inv_wl, steps, qlo, qhi);
+    // a distance cannot become negative: a leaf is no closer to the target than max(0, D - reach)
+    return base0 - T(kWd) * fmin(reach, D) + quad_min_range<T>(T(2) * ep, k.wl * qlo, k.wl * qhi) +
+           quad_min<T>(T(-2) * hp, k.wh * steps * k.dphimax);
+}
+
 MPCB_HD double lower_bound_from(const LaunchArgs &a, const SolveParams &P, double rx, double ry,
                                                    double D, double nx, double ny, double ch, double sh, double ep,
                                                    double hp, double base0, int steps) {
-    double lo, reach, qlo, qhi;
-    if (D > 0.0) {
-        const double inv = 1.0 / D;
-        projection_range(a, (rx * ch + ry * sh) * inv, fabs(rx * sh - ry * ch) * inv, steps, lo, reach);
-    } else {
-        reach = steps * a.g.smax;
-    }
-    const double invl = 1.0 / P.wl;
-    projection_range(a, (nx * ch + ny * sh) * invl, fabs(nx * sh - ny * ch) * invl, steps, qlo, qhi);
-    // a distance cannot become negative: a leaf is no closer to the target than max(0, D - reach)
-    return base0 - kWd * fmin(reach, D) + quad_min_range(2.0 * ep, P.wl * qlo, P.wl * qhi) +
-           quad_min(-2.0 * hp, P.wh * steps * a.g.dphimax);
+    return lower_bound_from_t<double>(bound_consts<double>(a, P, steps), rx, ry, D, nx, ny, ch, sh, ep, hp, base0, steps);
 }
 
-// ... for a node at (xi, eta, psi) with heading (cp, sp) in the start frame
+// ... for a node at (xi, eta, psi) with heading (cp, sp) in the start frame, from the solve's start-frame quantities
+// (u0, w0 target, d0 its distance, e0 scaled line distance, (nx0, ny0) its gradient, hp0 scaled heading error)
+template <typename T>
+MPCB_HD T subtree_lower_bound_t(const BoundConsts<T> &k, T u0, T w0, T d0, T e0, T nx0, T ny0, T hp0, T xi, T eta, T psi,
+                                T cp, T sp, int steps) {
+    const T relx = u0 - xi, rely = w0 - eta;
+    const T D = sqrt(relx * relx + rely * rely);
+    const T dl = nx0 * xi + ny0 * eta;                    // ep - e0
+    const T ep = e0 + dl;
+    const T dh = -k.wh * psi;                             // hp - hp0
+    const T hp = hp0 + dh;
+    const T base0 = T(kWd) * (D - d0) + dl * (ep + e0) + dh * (hp + hp0);
+    return lower_bound_from_t<T>(k, relx, rely, D, nx0, ny0, cp, sp, ep, hp, base0, steps);
+}
+
 MPCB_HD double subtree_lower_bound(const LaunchArgs &a, const SolveParams &P, double xi, double eta,
                                                       double psi, double cp, double sp, int steps) {
-    const double relx = P.u0 - xi, rely = P.w0 - eta;
-    const double D = sqrt(relx * relx + rely * rely);
-    const double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
-    const double hp = P.hp0 - P.wh * psi;
-    const double base0 = kWd * (D - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
-    return lower_bound_from(a, P, relx, rely, D, P.nx0, P.ny0, cp, sp, ep, hp, base0, steps);
+    return subtree_lower_bound_t<double>(bound_consts<double>(a, P, steps), P.u0, P.w0, P.d0, P.e0, P.nx0, P.ny0, P.hp0, xi, eta,
+                                         psi, cp, sp, steps);
+}
+
+// fp32 PRE-FILTER of the pruned pass 1: the same bound over the children of a depth-(H-1) node evaluated in float from
+// a float walk.  It decides nothing on its own: a node is dropped early only if  lb32 > bound + 8 tol1 , and
+//   |lb32 - lb64| <= 2^-24 [kWd (8 Dmax + 6 smax) + 16 Q(2E + Q) + 10 G(2H + G)] <= tol1
+// (the roundings of u0, w0, the walk, D, the three differences of squares and the two projected ranges, with
+// Dmax = d0 + H smax, E, H the anchor bounds and Q, G the one-step offsets of prep_kernel's error model; tol1 =
+// 2^-22 [4 kWd Dmax + 2 kWd smax + 5 (E+Q)^2 + 4 (H+G)^2]), so every node it drops the float64 test drops too and the set of
+// nodes that are scored -- and every number downstream -- is unchanged; it only spares the float64 set-up of the 99.9 %
+// of the nodes that are nowhere near the bound.
+struct Prefilter32 {
+    BoundConsts<float> k;
+    float u0, w0, d0, e0, nx0, ny0, hp0;
+};
+
+MPCB_HD Prefilter32 prefilter32(const LaunchArgs &a, const SolveParams &P) {
+    Prefilter32 f;
+    f.k = bound_consts<float>(a, P, 1);
+    f.u0 = (float)P.u0; f.w0 = (float)P.w0; f.d0 = (float)P.d0; f.e0 = (float)P.e0;
+    f.nx0 = (float)P.nx0; f.ny0 = (float)P.ny0; f.hp0 = (float)P.hp0;
+    return f;
+}
+
+MPCB_HD float node_prefilter32(const Prefilter32 &f, float xi, float eta, float psi, float cp, float sp) {
+    return subtree_lower_bound_t<float>(f.k, f.u0, f.w0, f.d0, f.e0, f.nx0, f.ny0, f.hp0, xi, eta, psi, cp, sp, 1);
 }
 
 }  // namespace mpcb

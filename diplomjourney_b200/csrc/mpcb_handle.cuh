@@ -40,7 +40,7 @@ struct mpcb_handle_s {
     std::vector<double> hv, hb;         // host copy of the raw grids
     double L = 0, delta_t = 0, v_min = 0, v_slow = 0;
     mpcb::GridTables g{};
-    mpcb::DevBuf tab64, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, leaf32r, ctl32, ctl32_slow;
+    mpcb::DevBuf tab64, tab32, vtab, tab64_slow, vtab_slow, beta, leaf32, leaf32p, leaf32r, ctl32, ctl32_slow;
     // options
     double tol_scale = 1.0;
     int algo = MPCB_ALGO_AUTO;
@@ -52,6 +52,7 @@ struct mpcb_handle_s {
     unsigned long long frontier_cap = mpcb::kFrontierCap;   // entries per frontier list (option, diagnostics: a tiny value forces the fallback)
     int subtree_cut = 2;       // pruned pass 1, H >= 3: 0 off, 1 depth-(H-2) bound per 256-node tile, 2 auto (frontier descent from the root for trees of more than one tile batch), 3 frontier always
     int screen = 1;       // exhaustive prefix pass 1 (prune = 0): 1 = screen loop without MUFU + rare full re-run, 0 = sqrt per leaf
+    int prefilter = 1;    // pruned pass 1: fp32 pre-filter before the float64 node set-up (identical results)
     int prune = 1;        // exact branch-and-bound in the prefix kernel (identical results, fewer leaves evaluated)   // host-API HELD solves with few candidates take the one-launch float64 path
     // scratch
     mpcb::DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list, reduce_scratch;

@@ -186,11 +186,17 @@ __device__ __forceinline__ float leaf_walk_direct(float xi, float eta, float psi
     return acc;
 }
 
-// float64 walk of the prefix (i_0 .. i_{H-2}) of depth-(H-1) node p in the start frame, then the
-// node's frame quantities.  Returns base_p (float64) and whether the node has not moved at all.
-__device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
-                                               unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved,
-                                               double *lower_bound = nullptr, double *base_direct = nullptr) {
+// A depth-(H-1) node in float64: its pose from the walk of its prefix (i_0 .. i_{H-2}) in the start frame, and the
+// quantities of its own frame that its children's costs (and the bound over them) are built from.
+struct NodeFrame {
+    double u, w, Dp;           // target in the node's frame, its distance
+    double ep, nu, nw;         // scaled line distance of the node, gradient of the scaled line distance in the node's frame
+    double hp;                 // scaled heading error
+    double base0;              // J_rel of the node's own terms: kWd (Dp - d0) + (ep^2 - e0^2) + (hp^2 - hp0^2)
+    bool unmoved;              // the node has not moved at all (the reference's "on the line origin" special case)
+};
+
+__device__ __forceinline__ void node_frame(const LaunchArgs &a, const SolveParams &P, unsigned long long p, NodeFrame &f) {
     double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
     unsigned long long rem = p;
     const int D = a.H - 1;
@@ -199,32 +205,52 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
         rem -= i * a.fd[k + 1].d;
         walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
     }
-    unmoved = (xi == 0.0 && eta == 0.0);
-    double relx = P.u0 - xi, rely = P.w0 - eta;
-    double u = cp * relx + sp * rely, w = cp * rely - sp * relx;
-    double Dp = sqrt(u * u + w * w);
-    double ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
-    double nu = cp * P.nx0 + sp * P.ny0, nw = cp * P.ny0 - sp * P.nx0;
-    double hp = P.hp0 - P.wh * psi;
-    pr.u = (float)u; pr.w = (float)w;
-    pr.u2 = (float)(-2.0 * u); pr.w2 = (float)(-2.0 * w);
-    const double dp_rem = split_distance(Dp, pr);
-    pr.nu = (float)nu; pr.nw = (float)nw;
-    pr.e2 = (float)(2.0 * ep); pr.h2 = (float)(2.0 * hp);
-    near = !(Dp >= 4.0 * a.g.smax);
+    f.unmoved = (xi == 0.0 && eta == 0.0);
+    const double relx = P.u0 - xi, rely = P.w0 - eta;
+    f.u = cp * relx + sp * rely; f.w = cp * rely - sp * relx;
+    f.Dp = sqrt(f.u * f.u + f.w * f.w);
+    f.ep = P.e0 + P.nx0 * xi + P.ny0 * eta;
+    f.nu = cp * P.nx0 + sp * P.ny0; f.nw = cp * P.ny0 - sp * P.nx0;
+    f.hp = P.hp0 - P.wh * psi;
     // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
-    const double base0 = kWd * (Dp - P.d0) + (ep - P.e0) * (ep + P.e0) + (hp - P.hp0) * (hp + P.hp0);
-    // no child can do better than: one step as straight at the target as the steering allows, the most favourable
-    // line offset that step can produce and the most favourable heading offset (lower_bound_from)
+    f.base0 = kWd * (f.Dp - P.d0) + (f.ep - P.e0) * (f.ep + P.e0) + (f.hp - P.hp0) * (f.hp + P.hp0);
+}
+
+// no child can do better than: one step as straight at the target as the steering allows, the most favourable line offset
+// that step can produce and the most favourable heading offset (lower_bound_from); in the node's own frame the heading
+// is (1, 0), the target (u, w), the line gradient (nu, nw)
+__device__ __forceinline__ double node_lower_bound(const LaunchArgs &a, const SolveParams &P, const NodeFrame &f) {
+    return lower_bound_from(a, P, f.u, f.w, f.Dp, f.nu, f.nw, 1.0, 0.0, f.ep, f.hp, f.base0, 1);
+}
+
+// the fp32 registers of a node that survived (the conversions are only paid for nodes whose children are scored);
+// returns base_p (with the remainder term of a NEAR node) and, for the direct form, base_direct
+__device__ __forceinline__ double node_regs(const LaunchArgs &a, const NodeFrame &f, ParentRegs &pr, bool &near,
+                                            double *base_direct) {
+    pr.u = (float)f.u; pr.w = (float)f.w;
+    pr.u2 = (float)(-2.0 * f.u); pr.w2 = (float)(-2.0 * f.w);
+    const double dp_rem = split_distance(f.Dp, pr);
+    pr.nu = (float)f.nu; pr.nw = (float)f.nw;
+    pr.e2 = (float)(2.0 * f.ep); pr.h2 = (float)(2.0 * f.hp);
+    near = !(f.Dp >= 4.0 * a.g.smax);
     if (base_direct) {
         pr.eh = 0.5f * pr.e2; pr.nhh = -0.5f * pr.h2;
-        pr.u2s = (float)(-2.0 * kWd * kWd * u); pr.w2s = (float)(-2.0 * kWd * kWd * w);
-        pr.D2s = (float)(kWd * kWd * (Dp * Dp));
-        *base_direct = base0 - kWd * Dp - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
+        pr.u2s = (float)(-2.0 * kWd * kWd * f.u); pr.w2s = (float)(-2.0 * kWd * kWd * f.w);
+        pr.D2s = (float)(kWd * kWd * (f.Dp * f.Dp));
+        *base_direct = f.base0 - kWd * f.Dp - (double)pr.eh * (double)pr.eh - (double)pr.nhh * (double)pr.nhh;
     }
-    if (lower_bound)   // in the node's own frame the heading is (1, 0), the target (u, w), the line gradient (nu, nw)
-        *lower_bound = lower_bound_from(a, P, u, w, Dp, nu, nw, 1.0, 0.0, ep, hp, base0, 1);
-    return base0 + (near ? dp_rem : 0.0);
+    return f.base0 + (near ? dp_rem : 0.0);
+}
+
+// all of it at once.  Returns base_p (float64) and whether the node has not moved at all.
+__device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveParams &P,
+                                               unsigned long long p, ParentRegs &pr, bool &near, bool &unmoved,
+                                               double *lower_bound = nullptr, double *base_direct = nullptr) {
+    NodeFrame f;
+    node_frame(a, P, p, f);
+    unmoved = f.unmoved;
+    if (lower_bound) *lower_bound = node_lower_bound(a, P, f);
+    return node_regs(a, f, pr, near, base_direct);
 }
 
 // pose of depth-(H-1) node p (FULL): the shared prefix of all its children, walked once per thread
@@ -587,7 +613,7 @@ prefix_kernel(const LaunchArgs a) {
             seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile_lo : tile_lo / a.tps));
         } else if (listed) {
             const unsigned long long g = a.tile_list[w];
-            n = (long long)(g / a.tiles_per_solve);
+            n = (long long)a.fd_tiles.div(g);
             tile_lo = g - (unsigned long long)n * a.tiles_per_solve;
             tile_hi = tile_lo + 1;
             seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile_lo : tile_lo / a.tps));
@@ -615,15 +641,43 @@ prefix_kernel(const LaunchArgs a) {
             bool near = false, unmoved = false;
             double base = 0.0, base_direct = 0.0, lb = -INFINITY;
             bool active = in_range;
-            if (active) base = parent_setup(a, P, p, pr, near, unmoved, &lb, PASS == 1 ? &base_direct : nullptr);
+            // Pruned pass 1: an fp32 pre-filter first (float walk, the same bound in float, a margin of 8 tol1 -- it only
+            // drops nodes the float64 test below would drop as well, mpcb_bounds.cuh), because all but a fraction of a per
+            // cent of the nodes of a listed tile are nowhere near the bound and the float64 set-up is most of this kernel.
+            unsigned pre_cut = 0;
+            if (PASS == 1 && PRUNE && a.prefilter) {
+                bool far = false;
+                const Prefilter32 pf = prefilter32(a, P);          // per solve: uniform over the work item
+                if (active) {
+                    float xi = 0.f, eta = 0.f, psi = 0.f, cp = 1.f, sp = 0.f;
+                    unsigned long long rem = p;
+                    for (int k = 0; k + 1 < a.H; ++k) {
+                        const unsigned long long i = a.fd[k + 1].div(rem);
+                        rem -= i * a.fd[k + 1].d;
+                        const float4 t = __ldg(a.g.tab32 + i);
+                        walk_step_t<float>(t.x, t.y, t.z, t.w, xi, eta, psi, cp, sp);
+                    }
+                    const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
+                    far = node_prefilter32(pf, xi, eta, psi, cp, sp) > __double2float_ru(bound + 8.0 * P.tol1);
+                }
+                pre_cut = __ballot_sync(0xffffffffu, far);
+                if (far) active = false;
+            }
+            // the node's frame and the bound over its children; the fp32 registers only for nodes that survive
+            NodeFrame f;
+            if (active) { node_frame(a, P, p, f); unmoved = f.unmoved; lb = node_lower_bound(a, P, f); }
             if (PASS == 2 && active && lb > tau + P.tol) active = false;   // no child can lie inside the window
             if (PASS == 1 && PRUNE) {
                 const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
                 const bool cut = active && lb > bound;
-                const unsigned m = __ballot_sync(0xffffffffu, cut);
+                const unsigned m = __ballot_sync(0xffffffffu, cut) | pre_cut;
                 if ((tid & 31) == 0 && m) atomicAdd(a.counters + 2, (unsigned long long)__popc(m));
                 active = active && !cut;
             }
+            // a warp none of whose nodes survived has nothing to score, publish or tighten (almost every warp of a listed
+            // tile: the rest of the iteration is warp-level only when the table is resident, so the warp may leave it)
+            if (PASS == 1 && PRUNE && single && !__any_sync(0xffffffffu, active)) continue;
+            if (active) base = node_regs(a, f, pr, near, PASS == 1 ? &base_direct : nullptr);
             const bool special = active && origin_case && unmoved;
             if (PASS == 1 && !(near || special)) base = base_direct;   // the packed loop ranks in the direct form
             double ex = 0.0, ey = 0.0, ephi = 0.0;
@@ -893,7 +947,7 @@ __global__ void __launch_bounds__(kThreads) frontier_expand_kernel(const LaunchA
 // the pruned pass-1 kernels then walk.  Exactness: same argument as the per-node cut.
 // does 256-node tile g (global tile number n * tiles_per_solve + tile) survive the depth-(H-2) bound?
 __device__ __forceinline__ bool tile_survives(const LaunchArgs &a, unsigned long long g, unsigned &cut_nodes) {
-    const unsigned long long n = g / a.tiles_per_solve, tile = g - n * a.tiles_per_solve;
+    const unsigned long long n = a.fd_tiles.div(g), tile = g - n * a.tiles_per_solve;
     const SolveParams &P = a.sp[n];
     cut_nodes = 0;
     if (P.flags & kFlagSkip) return false;
@@ -902,7 +956,8 @@ __device__ __forceinline__ bool tile_survives(const LaunchArgs &a, unsigned long
     const unsigned long long p_hi = min(p_lo + (unsigned long long)kThreads, a.u_end);     // exclusive
     const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
     bool keep = false;
-    for (unsigned long long q = p_lo / S; q <= (p_hi - 1) / S && !keep; ++q) {
+    const unsigned long long q_hi = a.fd_S.div(p_hi - 1);
+    for (unsigned long long q = a.fd_S.div(p_lo); q <= q_hi && !keep; ++q) {
         double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
         unsigned long long rem = q;
         for (int k = 0; k < a.H - 2; ++k) {           // fd[k + 2].d = S^(H-3-k): digits of a depth-(H-2) node
@@ -976,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 4) tilewalk_fallback_kernel(const La
         __syncthreads();
         for (unsigned t = 0; t < total; ++t) {
             const unsigned long long gt = s_tiles[t];
-            const long long n = (long long)(gt / a.tiles_per_solve);
+            const long long n = (long long)a.fd_tiles.div(gt);
             const unsigned long long tile = gt - (unsigned long long)n * a.tiles_per_solve;
             const unsigned seg = (unsigned)((unsigned long long)n * a.segs_per_solve + (a.tps == 1 ? tile : tile / a.tps));
             const SolveParams &P = a.sp[n];
@@ -1090,7 +1145,7 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
             in_q = c < (unsigned)S;
         } else if (listed) {
             const unsigned long long g = a.tile_list[ww / (kThreads / 32)];
-            n = (long long)(g / a.tiles_per_solve);
+            n = (long long)a.fd_tiles.div(g);
             wt = (g - (unsigned long long)n * a.tiles_per_solve) * (kThreads / 32) + ww % (kThreads / 32);
             if (wt >= wtps) continue;                                     // ragged last tile
         } else {
@@ -1406,6 +1461,7 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
     P.threshold = threshold ? threshold[n] : INFINITY;
     P.wl = cost_kind == 0 ? 10.0 : 100.0;
     P.wh = cost_kind == 0 ? 3.16227766016837952 : 0.0;
+    P.inv_wl = 1.0 / P.wl;
     double s0, c0;
     sincos(P.phi0, &s0, &c0);
     const double rx = P.xt - P.xs, ry = P.yt - P.ys;

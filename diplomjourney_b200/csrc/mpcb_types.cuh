@@ -89,6 +89,7 @@ struct GridTables {
     // float64, for the depth-(H-1) prefix walk and the exact re-evaluation
     const double4 *tab64;       // {cos dphi_c, sin dphi_c, s_c = v_c*dt, dphi_c}
     const double  *vtab;        // v_c
+    const float4  *tab32;       // tab64 rounded to float: the walk of the fp32 pre-filter (pruned pass 1)
     const double4 *tab64_slow;  // same with every v := max(min V, v_min)   (math_model_tree.py:312-316)
     const double  *vtab_slow;
     const double  *beta;        // beta[nb]
@@ -119,6 +120,7 @@ struct __align__(16) SolveParams {
     double e0, nx0, ny0;        // wl * signed line distance of the start, and its gradient
     double hp0;                 // wh * (theta - phi0)
     double wl, wh;              // sqrt of the line / heading weights
+    double inv_wl;              // 1 / wl (the bounds normalise the line gradient by it)
     double Kbase;               // kWd d0 + e0^2 + hp0^2 (cost terms of the start pose): J = Kbase + J_rel
     double tol;                 // 2 x error bound of the fp32 leaf value that pass 2 filters with (leaf_val / leafwalk)
     double tol1;                // 2 x error bound of the value pass 1 RANKS with (prefix: direct form; else = tol)
@@ -137,6 +139,7 @@ struct LaunchArgs {
     const SolveParams *sp;
     FastDiv64 fd[kMaxH];        // fd[k].d = S^(H-1-k)
     FastDiv32 fd32[kMaxH];      // same divisors, valid when idx32 != 0 (every index and divisor < 2^32)
+    FastDiv64 fd_tiles, fd_S;   // division by tiles_per_solve and by S (the pruned kernels decode a global tile number per tile)
     int idx32;
     unsigned step_digits[kMaxH]; // base-S digits of kThreads (most significant first): leafwalk advances a leaf index by kThreads
     int lw_smem;                // leafwalk FULL: stage ctl32 in shared memory (S <= 4096)
@@ -156,6 +159,7 @@ struct LaunchArgs {
     unsigned long long *counters;          // [0] refine segments, [1] candidates, [2] pruned depth-(H-1) nodes, [3] same, frontier descent (added to [2] when the descent completes)
     unsigned long long *ub;                // [N] ordered key of an upper bound on each solve's minimal J_rel (pruning), or null
     int prune;
+    int prefilter;                         // pruned pass 1: fp32 pre-filter of the node bound (mpcb_bounds.cuh)
     int screen;                            // exhaustive prefix pass 1: 0 = MUFU.SQRT per leaf, 1 = screened (sqrt only on nodes that can matter)
     double cosk[kMaxH], sink[kMaxH];       // cos / sin of (i+1) dphi_max: the heading range reachable in i+1 steps (cos = -2: the whole circle)
     // subtree cut (pruned pass 1, H >= 3): tiles that survived the depth-(H-2) bound, as global tile numbers

@@ -109,6 +109,9 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * of the node may have and still beat the solve's upper bound (an exact probe of the S held sequences, tightened by
  * every node that found something), a leaf matters iff t = cn - q^2 - gg^2 > 0 and fma(t, t, -dd) > 0; such nodes are
  * re-run with the square roots.  0: one MUFU.SQRT per leaf, no upper bound involved),
+ * "prefilter" (1, default; identical results: in the pruned pass 1 a node's bound is first evaluated in fp32 from an fp32
+ * walk and the node dropped if that exceeds the upper bound by a margin of 8 error bounds -- which the float64 test would
+ * do as well -- so that the float64 set-up is only paid by nodes near the bound; 0 = float64 test for every node),
  * "candidate_list" (entries, default 2^20; identical results: the refinement pass lists the leaves whose fp32 value lies
  * inside the error window and a second kernel evaluates them in float64 one thread each; candidates beyond the capacity
  * -- or all of them with 0 -- are evaluated by the thread that found them),

@@ -173,7 +173,19 @@ def shipped_bound():
         out = np.empty_like(xi)
         p = lambda a: a.ctypes.data_as(dp)
         lib.mpcb_test_subtree_lower_bounds(smax, smin, dmax, p(solve), len(xi), p(xi), p(eta), p(psi), k, p(out))
+        if k == 1:          # ... and the fp32 pre-filter of the pruned pass 1 on the same nodes, with the model's error bound
+            out32 = np.empty(len(xi), np.float32)
+            lib.mpcb_test_prefilter32(smax, smin, dmax, p(solve), len(xi), p(xi), p(eta), p(psi),
+                                      out32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+            H = 3
+            Rtot = H * smax
+            E1 = abs(e0) + wl * Rtot + wl * smax
+            H1 = abs(hp0) + wh * H * dmax + wh * dmax
+            Dmax = d0 + Rtot
+            tol1 = 2.0 ** -22 * (4e4 * Dmax + 2e4 * smax + 5 * E1 * E1 + 4 * H1 * H1)      # prep_kernel's tol1 (prefix)
+            bound.prefilter = (out32.astype(np.float64), out, tol1)
         return kbase + out
+    lib.mpcb_test_prefilter32.argtypes = [ctypes.c_double] * 3 + [dp, ctypes.c_longlong, dp, dp, dp, ctypes.POINTER(ctypes.c_float)]
     return bound
 
 
@@ -194,3 +206,26 @@ def test_shipped_bound_code_never_exceeds_the_true_minimum(shipped_bound, grid, 
             scale = max(1.0, np.abs(true_min[ok]).max())
             assert (true_min[ok] - lb[ok]).min() >= -1e-10 * scale, (grid, k, (true_min[ok] - lb[ok]).min())
             np.testing.assert_allclose(lb[ok], new[ok], rtol=0, atol=1e-8 * scale)
+
+
+@pytest.mark.parametrize("grid", sorted(GRIDS))
+@pytest.mark.parametrize("cost", [C.COST_MM, C.COST_TREE])
+def test_fp32_prefilter_stays_within_its_margin_of_the_float64_bound(shipped_bound, grid, cost):
+    """The pruned pass 1 drops a node early when the bound evaluated in FLOAT exceeds the upper bound by 8 tol1.  That is
+    only sound if |lb32 - lb64| stays (well) below 8 tol1: measured here on every depth-2 node of small trees with the
+    shipped code, including a robot next to its target and robots far from their line (large anchors)."""
+    V, B = GRIDS[grid]
+    sc = C.random_scenarios(10, 29)
+    sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]
+    sc[1, 3:5] = sc[1, :2] + [60.0, -45.0]                            # a far target: large kWd d
+    worst = 0.0
+    for x in sc:
+        new, true_min, poses, consts = _bounds(V, B, 3, x, 1, cost, want_poses=True)
+        shipped_bound(x, cost, poses, consts, 1)
+        lb32, lb64, tol1 = shipped_bound.prefilter
+        ok = np.isfinite(lb64)
+        err = np.abs(lb32[ok] - lb64[ok]).max()
+        worst = max(worst, err / tol1)
+        assert err <= tol1, (grid, cost, err, tol1)                   # the analysis in mpcb_bounds.cuh; the kernel allows 8x
+    assert worst > 0.0
+    print(f"fp32 pre-filter: worst |lb32 - lb64| = {worst:.3f} tol1 ({grid}, {cost})")
