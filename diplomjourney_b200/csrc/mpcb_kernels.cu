@@ -253,25 +253,6 @@ __device__ __forceinline__ double parent_setup(const LaunchArgs &a, const SolveP
     return node_regs(a, f, pr, near, base_direct);
 }
 
-// pose of depth-(H-1) node p (FULL): the shared prefix of all its children, walked once per thread
-__device__ __noinline__ void exact_prefix(const LaunchArgs &a, const SolveParams &P, unsigned long long p,
-                                          double &x, double &y, double &phi) {
-    x = P.xs; y = P.ys; phi = P.phi0;
-    unsigned long long rem = p;
-    for (int k = 0; k + 1 < a.H; ++k) {
-        unsigned long long c = a.fd[k + 1].div(rem);
-        rem -= c * a.fd[k + 1].d;
-        exact_step(a, a.g.tab64, a.g.vtab, c, x, y, phi);
-    }
-}
-
-// cost of child c of a node whose exact pose is known (same arithmetic as exact_cost's last step)
-__device__ __noinline__ double exact_child_cost(const LaunchArgs &a, const SolveParams &P, double x, double y,
-                                                double phi, unsigned c) {
-    exact_step(a, a.g.tab64, a.g.vtab, c, x, y, phi);
-    return exact_terminal(a, P, x, y, phi);
-}
-
 // candidate found by the refinement filter: listed for cand_eval_kernel (float64 evaluation, one thread per candidate:
 // the in-window leaves of a solve cluster in a few nodes, and a thread evaluating its node's candidates one after the
 // other -- three double-precision sincos each -- was most of pass 2); true = listed
@@ -680,8 +661,6 @@ prefix_kernel(const LaunchArgs a) {
             if (active) base = node_regs(a, f, pr, near, PASS == 1 ? &base_direct : nullptr);
             const bool special = active && origin_case && unmoved;
             if (PASS == 1 && !(near || special)) base = base_direct;   // the packed loop ranks in the direct form
-            double ex = 0.0, ey = 0.0, ephi = 0.0;
-            bool have_pose = false;
             float best = INFINITY;
             const float thr = PASS == 2 ? __double2float_ru(tau - base) : 0.f;
             const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);

@@ -34,12 +34,19 @@ def test_split_tree_two_ranks_nccl():
 def test_bench_two_ranks():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "bench.py"),
-                        "--gpus", "2", "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--gpus", "2", "--steps", "2", "--warmup", "3", "--cfg4-scenarios", "4096"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(line) == 1
     d = json.loads(line[0])
     assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] > 1e12
+    # the two multi-GPU configurations of the baseline ride on the same line: configs[3] strong-scaled (no collective) and
+    # configs[4], ONE tree split over the ranks and reconciled by the library's own NCCL all-gather
+    assert d["cfg4_strong"]["scaling"] == "strong" and d["cfg4_strong"]["exhaustive_check"]["identical"]
+    runs = d["split_tree"]["runs"]
+    assert {(r["H"], r["scenario"]) for r in runs} == {(6, "config.py"), (6, "tie-heavy"), (5, "config.py"), (5, "tie-heavy")}
+    assert all(r["ranks_agree"] for r in runs) and all(r["equals_one_gpu_whole_tree"] for r in runs if r["H"] == 6)
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
