@@ -545,13 +545,11 @@ __device__ __forceinline__ float prefix_min_loop_scalar(const float4 *__restrict
 // window are skipped lane by lane (a queue that compacts the survivors across tiles was measured 1.3-4x SLOWER:
 // it serialises the float64 set-up and the fp32 pair loop that otherwise overlap between warps).
 template <int PASS, bool HEAD, bool PRUNE = false, bool QMODE = false>
-// (pass 2 walks a short work list of tiles, each a chain of float64 set-up, filter and publication: it is latency-bound,
-//  so it runs at four CTAs per SM -- 64 registers -- rather than at the two its natural 116 registers allow)
+// (PASS is 1: the refinement pass of the prefix algorithm is refine_prefix_kernel)
 __global__ void __launch_bounds__((PASS == 1 && !PRUNE) ? kPrefixCta : kThreads, (PASS == 1 && !PRUNE) ? 1 : 4)
 prefix_kernel(const LaunchArgs a) {
+    static_assert(PASS == 1, "pass 2 of the prefix algorithm is refine_prefix_kernel");
     extern __shared__ float4 s_leaf[];
-    __shared__ double s_J[kThreads / 32];
-    __shared__ long long s_j[kThreads / 32];
     const int tid = threadIdx.x;
     const int S = a.g.S;
     const bool single = S <= kLeafChunk;
@@ -610,10 +608,7 @@ prefix_kernel(const LaunchArgs a) {
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;               // a robot that has already stopped (uniform per work item)
         const bool origin_case = (P.flags & kFlagStartIsOrigin) != 0;
-        const double tau = PASS == 2 ? a.tau[n] : 0.0;
-        if (PASS == 2 && tid == 0 && (a.tps == 1 || w % a.tps == 0)) atomicAdd(a.counters, 1ULL);
         double segbest = INFINITY;
-        double bJ = INFINITY; long long bj = -1;
         {
             const unsigned long long tile = tile_lo;
             const unsigned long long p = qmode ? p_q : a.u_begin + tile * kThreads + (tid % kThreads);
@@ -647,7 +642,6 @@ prefix_kernel(const LaunchArgs a) {
             // the node's frame and the bound over its children; the fp32 registers only for nodes that survive
             NodeFrame f;
             if (active) { node_frame(a, P, p, f); unmoved = f.unmoved; lb = node_lower_bound(a, P, f); }
-            if (PASS == 2 && active && lb > tau + P.tol) active = false;   // no child can lie inside the window
             if (PASS == 1 && PRUNE) {
                 const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
                 const bool cut = active && lb > bound;
@@ -662,7 +656,6 @@ prefix_kernel(const LaunchArgs a) {
             const bool special = active && origin_case && unmoved;
             if (PASS == 1 && !(near || special)) base = base_direct;   // the packed loop ranks in the direct form
             float best = INFINITY;
-            const float thr = PASS == 2 ? __double2float_ru(tau - base) : 0.f;
             const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
             // chunked tables: a tile whose nodes were all cut must not stream the table through shared memory
             const bool any_active = (PASS == 1 && PRUNE && !single) ? (__syncthreads_or(active) != 0) : true;
@@ -699,35 +692,6 @@ prefix_kernel(const LaunchArgs a) {
                                                  : prefix_min_loop_far2<HEAD>(s_leaf, npairs, pr, best);
                     continue;
                 }
-                if (PASS == 2) {
-                    // Refinement filter: of a listed tile's 256 nodes only the few whose bound reaches into the window are
-                    // still active, so -- as in the pruned pass 1 -- the warp takes them one at a time with the node's S
-                    // leaves spread over its lanes (a lane scanning its node alone kept the other 31 idle for S iterations).
-                    const int lane = tid & 31;
-                    for (unsigned todo = __ballot_sync(0xffffffffu, active); todo; todo &= todo - 1) {
-                        const int src = __ffs(todo) - 1;
-                        ParentRegs q;
-                        q.u = __shfl_sync(0xffffffffu, pr.u, src); q.w = __shfl_sync(0xffffffffu, pr.w, src);
-                        q.u2 = __shfl_sync(0xffffffffu, pr.u2, src); q.w2 = __shfl_sync(0xffffffffu, pr.w2, src);
-                        q.D2 = __shfl_sync(0xffffffffu, pr.D2, src); q.Dp = __shfl_sync(0xffffffffu, pr.Dp, src);
-                        q.nu = __shfl_sync(0xffffffffu, pr.nu, src); q.nw = __shfl_sync(0xffffffffu, pr.nw, src);
-                        q.e2 = __shfl_sync(0xffffffffu, pr.e2, src); q.h2 = __shfl_sync(0xffffffffu, pr.h2, src);
-                        const bool qnear = __shfl_sync(0xffffffffu, (int)near, src) != 0;
-                        const bool qspecial = __shfl_sync(0xffffffffu, (int)special, src) != 0;
-                        const float qLsp = __shfl_sync(0xffffffffu, Lspecial, src), qthr = __shfl_sync(0xffffffffu, thr, src);
-                        const double qbase = __shfl_sync(0xffffffffu, base, src);
-                        const unsigned long long qp = __shfl_sync(0xffffffffu, p, src);
-                        for (int c = lane; c < cn; c += 32) {
-                            const float4 t = s_leaf[c];
-                            float L = qnear ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, q)
-                                            : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, q);
-                            if (qspecial && t.z == 0.f) L = qLsp;
-                            if (L <= qthr)      // in-window leaf: listed for the float64 evaluation, or evaluated here if the list is full
-                                take_candidate(a, P, n, (long long)(qp * (unsigned long long)S + c0 + c), qbase + (double)L, bJ, bj);
-                        }
-                    }
-                    continue;
-                }
                 if (!active) continue;
                 {
                     const int npairs = (cn + 1) >> 1;
@@ -742,9 +706,102 @@ prefix_kernel(const LaunchArgs a) {
                 if ((tid & 31) == 0 && v < INFINITY) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol1));
             }
         }
-        if (PASS == 1 && qmode) publish_segmin_lanes(a, seg, segbest);
-        else if (PASS == 1) publish_segmin(a, seg, segbest);
-        else publish_best(a, n, bJ, bj, s_J, s_j);
+        if (qmode) publish_segmin_lanes(a, seg, segbest);
+        else publish_segmin(a, seg, segbest);
+    }
+}
+
+// ------------------------------------------------------------------------------------ prefix, pass 2 (refinement filter)
+// The listed tiles, WARP BY WARP: a work item is one 32-node slice of a listed 256-node tile.  Of those 32 nodes only
+// the few whose bound reaches into the window are live, and the warp scans them one at a time with the node's S leaves
+// spread over its lanes (a lane scanning its node alone kept the other 31 idle for S iterations; the warp-wide scan never
+// does more iterations than that).  In-window leaves go to the candidate list (or, if it is full, are evaluated on the
+// spot and folded into the solve's record under its lock).  No CTA barrier: with a whole tile per CTA seven of eight
+// warps waited at the barrier for the one that had something to scan (barrier stall 20 per issue, 9 % issue slots).
+__device__ __forceinline__ void publish_best_warp(const LaunchArgs &a, long long n, double bJ, long long bj) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oJ = __shfl_xor_sync(0xffffffffu, bJ, o);
+        const long long oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        lex_min(bJ, bj, oJ, oj);
+    }
+    if ((threadIdx.x & 31) == 0 && bj >= 0) {
+        while (atomicCAS(a.lock + n, 0, 1) != 0) {}
+        __threadfence();
+        double cJ = *(volatile double *)(a.bestJ + n);
+        long long cj = *(volatile long long *)(a.bestIdx + n);
+        lex_min(cJ, cj, bJ, bj);
+        *(volatile double *)(a.bestJ + n) = cJ;
+        *(volatile long long *)(a.bestIdx + n) = cj;
+        __threadfence();
+        atomicExch(a.lock + n, 0);
+    }
+}
+
+template <bool HEAD>
+__global__ void __launch_bounds__(kThreads, 4) refine_prefix_kernel(const LaunchArgs a) {
+    extern __shared__ float4 s_leaf[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int S = a.g.S;
+    const bool single = S <= kLeafChunk;
+    if (single) {
+        for (int i = tid; i < S; i += blockDim.x) s_leaf[i] = __ldg(a.g.leaf32 + i);
+        __syncthreads();
+    }
+    // a table that does not fit shared memory is read through L1/L2 (the lanes of a scan read consecutive entries)
+    const float4 *__restrict__ tab = single ? s_leaf : a.g.leaf32;
+    constexpr unsigned wpt = kThreads / 32;                                  // 32-node slices per tile
+    const unsigned long long nww = (unsigned long long)(*a.work_count) * a.tps * wpt;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * wpt + (tid >> 5);
+    const unsigned long long GW = (unsigned long long)gridDim.x * wpt;
+    for (unsigned long long ww = gw; ww < nww; ww += GW) {
+        const unsigned long long wt = ww / wpt;
+        const unsigned sub = (unsigned)(ww - wt * wpt);
+        unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
+        decode_work<2>(a, wt, seg, n, tile_lo, tile_hi);
+        if (lane == 0 && sub == 0 && (a.tps == 1 || wt % a.tps == 0)) atomicAdd(a.counters, 1ULL);
+        const SolveParams &P = a.sp[n];
+        if (P.flags & kFlagSkip) continue;
+        const double tau = a.tau[n];
+        const unsigned long long p = a.u_begin + tile_lo * kThreads + sub * 32u + lane;
+        bool active = tile_lo < tile_hi && p < a.u_end;
+        NodeFrame f;
+        if (active) {
+            node_frame(a, P, p, f);
+            if (node_lower_bound(a, P, f) > tau + P.tol) active = false;      // no child can lie inside the window
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, active);
+        if (!todo) continue;
+        ParentRegs pr = {};
+        bool near = false;
+        double base = 0.0;
+        if (active) base = node_regs(a, f, pr, near, nullptr);
+        const bool special = active && (P.flags & kFlagStartIsOrigin) && f.unmoved;
+        const float thr = __double2float_ru(tau - base);
+        const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+        double bJ = INFINITY; long long bj = -1;
+        for (; todo; todo &= todo - 1) {
+            const int src = __ffs(todo) - 1;
+            ParentRegs q;
+            q.u = __shfl_sync(0xffffffffu, pr.u, src); q.w = __shfl_sync(0xffffffffu, pr.w, src);
+            q.u2 = __shfl_sync(0xffffffffu, pr.u2, src); q.w2 = __shfl_sync(0xffffffffu, pr.w2, src);
+            q.D2 = __shfl_sync(0xffffffffu, pr.D2, src); q.Dp = __shfl_sync(0xffffffffu, pr.Dp, src);
+            q.nu = __shfl_sync(0xffffffffu, pr.nu, src); q.nw = __shfl_sync(0xffffffffu, pr.nw, src);
+            q.e2 = __shfl_sync(0xffffffffu, pr.e2, src); q.h2 = __shfl_sync(0xffffffffu, pr.h2, src);
+            const bool qnear = __shfl_sync(0xffffffffu, (int)near, src) != 0;
+            const bool qspecial = __shfl_sync(0xffffffffu, (int)special, src) != 0;
+            const float qLsp = __shfl_sync(0xffffffffu, Lspecial, src), qthr = __shfl_sync(0xffffffffu, thr, src);
+            const double qbase = __shfl_sync(0xffffffffu, base, src);
+            const unsigned long long qp = __shfl_sync(0xffffffffu, p, src);
+            for (int c = lane; c < S; c += 32) {
+                const float4 t = tab[c];
+                float L = qnear ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, q) : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, q);
+                if (qspecial && t.z == 0.f) L = qLsp;
+                if (L <= qthr)
+                    take_candidate(a, P, n, (long long)(qp * (unsigned long long)S + c), qbase + (double)L, bJ, bj);
+            }
+        }
+        if (__any_sync(0xffffffffu, bj >= 0)) publish_best_warp(a, n, bJ, bj);
     }
 }
 
@@ -1784,8 +1841,9 @@ cudaError_t launch_pass(cudaStream_t st, const LaunchArgs &a, int pass, bool pre
         if (pass == 1)
             return head ? launch_persistent(prefix_kernel<1, true>, a, pass, sm, sms, st, kPrefixCta)
                         : launch_persistent(prefix_kernel<1, false>, a, pass, sm, sms, st, kPrefixCta);
-        return head ? launch_persistent(prefix_kernel<2, true>, a, pass, sm, sms, st)
-                    : launch_persistent(prefix_kernel<2, false>, a, pass, sm, sms, st);
+        const size_t sm2 = sizeof(float4) * (size_t)(a.g.S <= kLeafChunk ? a.g.S : 0);       // pass 2 stages the per-leaf table
+        return head ? launch_persistent(refine_prefix_kernel<true>, a, pass, sm2, sms, st)
+                    : launch_persistent(refine_prefix_kernel<false>, a, pass, sm2, sms, st);
     }
     const int kind = a.mode == 1 ? 2 : (a.idx32 ? 1 : 0);
     const size_t lw_sm = (a.mode != 1 && a.lw_smem) ? sizeof(float2) * (size_t)a.g.S : 0;
