@@ -906,8 +906,15 @@ __global__ void __launch_bounds__(prefixn_cta(NPT), NPT / 2) prefixn_kernel(cons
                 if ((tid & 31) == 0) atomicMin(a.ub + n, ordered_key(v + 0.5 * P.tol1));
             }
         }
+        // SCREEN: a node whose best value lies above the bound cannot hold the minimum or an in-window leaf, whichever loop
+        // scored it (nodes in the NEAR regime or on the line origin are not screened leaf by leaf) -- it publishes nothing.
+        // Otherwise a share of a split tree that holds no leaf near the bound would build its refinement window around
+        // such nodes: on the config.py tree the 16^4 exactly tied unmoved nodes of the v = 0 share, 2.3e7 candidates.
 #pragma unroll
-        for (int k = 0; k < NPT; ++k) publish_segmin(a, seg[k], active[k] ? base[k] + (double)best[k] : INFINITY);
+        for (int k = 0; k < NPT; ++k) {
+            const double v = active[k] ? base[k] + (double)best[k] : INFINITY;
+            publish_segmin(a, seg[k], (!SCREEN || v <= ubw) ? v : INFINITY);
+        }
     }
 }
 

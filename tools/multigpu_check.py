@@ -58,6 +58,17 @@ oc = torch.tensor([float("nan")], dtype=torch.float64, device="cuda"); oi = torc
 comm.allreduce_min(oc.data_ptr(), oi.data_ptr()); s.sync()
 ok = ok and np.isnan(float(oc[0])) and int(oi[0]) == -1
 
+# a share that holds no leaf near the optimum must not build a refinement window of its own: on the config.py tree the share
+# of the v = 0 first controls holds 16^(H-1) exactly tied unmoved nodes (once 2.3e7 float64 candidates on that rank)
+from diplomjourney_b200 import config as cfg
+s.set_option("prune", 0)
+r = s.solve_tree_split(comm, nat.COST_MM, 4, [cfg.x_0, cfg.y_0, cfg.phi_0], [cfg.x_t, cfg.y_t], [cfg.x_0, cfg.y_0])
+cands = [None] * world
+dist.all_gather_object(cands, s.stats()["refine_candidates"])
+ok = ok and int(r["index"][0]) == s.S ** 4 - 1 and sum(cands) <= 64
+if rank == 0:
+    print(f"world={world} config.py tree H=4, every leaf evaluated: float64 candidates per rank {cands}", flush=True)
+
 x = sc[0]
 oc = torch.empty(1, dtype=torch.float64, device="cuda"); oi = torch.empty(1, dtype=torch.int64, device="cuda")
 st = torch.tensor(x[:3].copy(), device="cuda"); tg = torch.tensor(x[3:5].copy(), device="cuda"); og = torch.tensor(x[:2].copy(), device="cuda")
