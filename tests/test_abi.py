@@ -71,3 +71,22 @@ def test_every_option_the_library_accepts_is_documented_in_the_header():
     header = open(os.path.join(ROOT, "include", "mpcb200.h")).read()
     for name in accepted:
         assert f'"{name}"' in header, f"option {name} is not described in include/mpcb200.h"
+
+
+def test_bench_line_helpers():
+    """bench.py without a GPU: both arms describe the workload with the same `config` object, the per-rollout operation
+    counts cover every kernel the line can name, and the roofline's ncu figures come from a committed capture."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = bench.workload("cfg2")
+    cfg = bench.config_of(wl)
+    assert cfg["S"] == 451 and cfg["H"] == 3 and cfg["robots_per_gpu"] == 1024 and cfg["leaves_per_solve"] == 451 ** 3
+    assert set(bench.EXECUTED) == {"prefix_screen", "prefix_full", "leafwalk"}
+    for key in bench.EXECUTED:
+        rec = bench.ncu_record(key)
+        assert rec is not None and os.path.exists(os.path.join(ROOT, rec["file"])) and rec["traffic"] > 0, key
+        assert 0 < rec["fma_pipe_pct"] < 100 and 0 < rec["xu_pipe_pct"] < 100
+    pins = bench.pinned_bigtree()
+    assert {name for name, _, _ in bench.BIGTREES} == set(pins) and all(p["ranks_agree"] for p in pins.values())

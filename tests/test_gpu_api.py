@@ -239,3 +239,29 @@ def test_device_closed_loop_many_robots_per_cta():
     assert nat.LOOP_ON_TARGET in set(np.unique(big["status"]))
     assert np.isnan(big["log"][0, big["ticks"][0]:]).all() and not np.isnan(big["log"][0, :big["ticks"][0]]).any()
     s.close()
+
+
+def test_held_tick_one_call_equals_the_two_call_path():
+    """mpcb_held_tick_host (window lists + HELD solve in one call; inputs and results in mapped pinned host memory) ==
+    set_grid + solve, with the staged-copy flavour and with the slow-down override, on ticks of the reference run."""
+    from diplomjourney_b200 import config
+    nat, _ = _window_params()
+    mt = importlib.import_module("diplomjourney_b200.math_model_tree")
+    s = nat.Solver(0)
+    rng = np.random.default_rng(11)
+    for k in range(24):
+        v, beta = rng.uniform(0.0, 0.99), rng.uniform(-1.0, 1.0)
+        V, B = mt.vector_of_velocities(v), mt.vector_of_beta_angles(beta)
+        st, tg, og = rng.uniform(-3, 3, 3), rng.uniform(-3, 3, 2), rng.uniform(-1, 1, 2)
+        thr = float("inf") if k % 5 else 1.0
+        flags = nat.FLAG_SLOW if k % 3 == 0 else 0
+        s.set_grid(V, B, config.L, config.delta_t, config.v_min)
+        ref = s.solve(nat.MODE_HELD, nat.COST_TREE, 3, st, tg, og, threshold=thr, flags=flags)
+        for zc in (1, 0):
+            s.set_option("zero_copy", zc)
+            cost, idx, traj, ctl = s.held_tick(V, B, config.L, config.delta_t, config.v_min, nat.COST_TREE, 3, st, tg, og, thr, flags)
+            assert (cost, idx) == (ref["cost"][0], ref["index"][0])
+            np.testing.assert_array_equal(traj, ref["traj"][0])
+            assert ctl == tuple(ref["first_control"][0])
+    s.set_option("zero_copy", 1)
+    s.close()
