@@ -57,6 +57,14 @@ class LoopParams(C.Structure):
 
 LOOP_ON_TARGET, LOOP_STALLED, LOOP_MAX_TICKS, LOOP_NO_LEAF = 0, 1, 2, 3
 
+
+class LoopEvent(C.Structure):
+    """mpcb_loop_event (include/mpcb200.h): one operator event of a closed-loop script."""
+    _fields_ = [("tick", C.c_int32), ("kind", C.c_int32), ("a", C.c_double), ("b", C.c_double)]
+
+
+EVENT_NEW_TARGET, EVENT_TURN_LEFT, EVENT_TURN_RIGHT = 1, 2, 3
+
 _lib = None
 _dp, _i64p, _u8p, _fp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.POINTER(C.c_float)
 
@@ -93,6 +101,7 @@ def load():
     loop = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.mpcb_held_closed_loop_host.argtypes = loop
     lib.mpcb_held_closed_loop_device.argtypes = loop
+    lib.mpcb_held_closed_loop_events_host.argtypes = loop[:8] + [vp, C.c_int32, C.c_double] + loop[8:] + [vp]
     lib.mpcb_held_tick_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                         vp, vp, vp, C.c_double, C.c_int, vp, vp, vp, vp]
     win = [vp, C.POINTER(LoopParams), C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -283,9 +292,13 @@ class Solver:
                                                        _ptr(ctl_o), _ptr(shape_o)))
         return dict(cost=cost_o, index=idx_o, traj=traj_o, first_control=ctl_o, shape=shape_o)
 
-    def held_closed_loop(self, params: "LoopParams", init, target, origin, first_threshold=None, slow_steps=None):
+    def held_closed_loop(self, params: "LoopParams", init, target, origin, first_threshold=None, slow_steps=None,
+                         events=None, radius_u_turn=0.0):
         """Whole closed loops of the online controller for a batch of robots on the device
-        (mpcb_held_closed_loop_host). Returns dict(log[N,max_ticks,5], ticks[N], status[N])."""
+        (mpcb_held_closed_loop_host / _events_host). ``events``: an operator script [(tick, kind, a, b), ...] with kind
+        EVENT_NEW_TARGET (a, b = the new target) or EVENT_TURN_LEFT / _RIGHT (a = distance), applied to every robot
+        after the tick it names; ``radius_u_turn`` = L / sin(beta_max) for the turns.
+        Returns dict(log[N,max_ticks,5], ticks[N], status[N], final[N,6] = x_t, y_t, x_0, y_0, steps_for_slowing, m)."""
         ini = _arr(init, np.float64, (-1, 5))
         N = ini.shape[0]
         tg = _arr(np.broadcast_to(np.asarray(target, np.float64).reshape(-1, 2), (N, 2)), np.float64)
@@ -295,9 +308,15 @@ class Solver:
         log = np.full((N, params.max_ticks, 5), np.nan)
         ticks = np.empty(N, np.int32)
         status = np.empty(N, np.int32)
-        self._ck(self.lib.mpcb_held_closed_loop_host(self.h, C.byref(params), N, _ptr(ini), _ptr(tg), _ptr(og), _ptr(thr),
-                                                     _ptr(sl), _ptr(log), _ptr(ticks), _ptr(status)))
-        return dict(log=log, ticks=ticks, status=status)
+        ev = (LoopEvent * max(1, len(events or ())))()
+        for i, (tick, kind, a, b) in enumerate(events or ()):
+            ev[i] = LoopEvent(int(tick), int(kind), float(a), float(b))
+        final = np.empty((N, 6))
+        self._ck(self.lib.mpcb_held_closed_loop_events_host(self.h, C.byref(params), N, _ptr(ini), _ptr(tg), _ptr(og),
+                                                            _ptr(thr), _ptr(sl), ev if events else None,
+                                                            len(events or ()), float(radius_u_turn), _ptr(log),
+                                                            _ptr(ticks), _ptr(status), _ptr(final)))
+        return dict(log=log, ticks=ticks, status=status, final=final)
 
     def full_closed_loop(self, cost, H, init_state, target, origin, first_threshold=None, eps=0.001, max_ticks=256):
         """Closed loop of the FULL-tree scripts for a batch of robots (mpcb_full_closed_loop_host): one batched

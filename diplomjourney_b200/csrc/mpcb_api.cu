@@ -277,7 +277,7 @@ int mpcb_destroy(mpcb_handle *h) {
                       &h->ctl32_slow, &h->sp, &h->segmin, &h->worklist, &h->misc, &h->tau, &h->bestJ, &h->bestIdx,
                       &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
-                      &h->loop_status, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
+                      &h->loop_status, &h->loop_events, &h->loop_final, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
                       &h->fl_count, &h->nccl_scratch, &h->cand, &h->cand_J, &h->cand_sel})
         b->release();
     if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -782,9 +782,11 @@ int mpcb_dump_leaves_host(mpcb_handle *h, int mode, int cost_kind, int H, int al
     return MPCB_OK;
 }
 
-int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
-                                 const double *target, const double *origin, const double *first_threshold,
-                                 const int32_t *slow_steps, double *out_log, int32_t *out_ticks, int32_t *out_status) {
+// device pointers throughout; events / out_final may be null
+static int held_loop_core(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
+                          const double *target, const double *origin, const double *first_threshold,
+                          const int32_t *slow_steps, const mpcb_loop_event *events, int n_events, double radius_u_turn,
+                          double *out_log, int32_t *out_ticks, int32_t *out_status, double *out_final) {
     if (!h || !p) return MPCB_ERR_INVALID;
     if (N < 0 || N >= (1LL << 31)) return fail(h, MPCB_ERR_INVALID, "N out of range");
     if (N == 0) return MPCB_OK;
@@ -798,6 +800,7 @@ int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params *p, int6
     a.p = *p; a.N = N;
     a.init = init; a.target = target; a.origin = origin; a.first_threshold = first_threshold;
     a.slow_steps = slow_steps; a.out_log = out_log; a.out_ticks = out_ticks; a.out_status = out_status;
+    a.events = events; a.n_events = events ? n_events : 0; a.radius_u_turn = radius_u_turn; a.out_final = out_final;
     CK(launch_held_loop(h->stream, a, h->sms));
     h->stats = mpcb_stats{};
     h->stats.kernel_launches = 1;
@@ -805,10 +808,31 @@ int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params *p, int6
     return MPCB_OK;
 }
 
+int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
+                                 const double *target, const double *origin, const double *first_threshold,
+                                 const int32_t *slow_steps, double *out_log, int32_t *out_ticks, int32_t *out_status) {
+    return held_loop_core(h, p, N, init, target, origin, first_threshold, slow_steps, nullptr, 0, 0.0, out_log, out_ticks,
+                          out_status, nullptr);
+}
+
 int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
                                const double *target, const double *origin, const double *first_threshold,
                                const int32_t *slow_steps, double *out_log, int32_t *out_ticks, int32_t *out_status) {
+    return mpcb_held_closed_loop_events_host(h, p, N, init, target, origin, first_threshold, slow_steps, nullptr, 0, 0.0,
+                                             out_log, out_ticks, out_status, nullptr);
+}
+
+int mpcb_held_closed_loop_events_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N, const double *init,
+                                      const double *target, const double *origin, const double *first_threshold,
+                                      const int32_t *slow_steps, const mpcb_loop_event *events, int32_t n_events,
+                                      double radius_u_turn, double *out_log, int32_t *out_ticks, int32_t *out_status,
+                                      double *out_final) {
     if (!h || !p) return MPCB_ERR_INVALID;
+    if (n_events < 0 || n_events > 4096 || (n_events > 0 && !events))
+        return fail(h, MPCB_ERR_INVALID, "closed loop: bad event script (n_events=%d)", n_events);
+    for (int e = 0; e < n_events; ++e)
+        if (events[e].kind < MPCB_EVENT_NEW_TARGET || events[e].kind > MPCB_EVENT_TURN_RIGHT)
+            return fail(h, MPCB_ERR_INVALID, "closed loop: event %d has unknown kind %d", e, events[e].kind);
     if (N <= 0) return N == 0 ? MPCB_OK : fail(h, MPCB_ERR_INVALID, "N < 0");
     if (!init || !target || !origin || !out_log || !out_ticks || !out_status)
         return fail(h, MPCB_ERR_INVALID, "closed loop: null pointer");
@@ -837,11 +861,19 @@ int mpcb_held_closed_loop_host(mpcb_handle *h, const mpcb_loop_params *p, int64_
         CK(cudaMemcpyAsync(h->in_flags.p, slow_steps, sizeof(int) * N, cudaMemcpyHostToDevice, st));
         d_slow = h->in_flags.as<int>();
     }
+    const mpcb_loop_event *d_events = nullptr;
+    if (n_events > 0) {
+        CK(h->loop_events.ensure(sizeof(mpcb_loop_event) * n_events));
+        CK(cudaMemcpyAsync(h->loop_events.p, events, sizeof(mpcb_loop_event) * n_events, cudaMemcpyHostToDevice, st));
+        d_events = h->loop_events.as<mpcb_loop_event>();
+    }
+    if (out_final) CK(h->loop_final.ensure(sizeof(double) * 6 * N));
     CK(cudaMemsetAsync(h->loop_log.p, 0xFF, sizeof(double) * nlog, st));     // NaN pattern for the rows no tick wrote
-    int rc = mpcb_held_closed_loop_device(h, p, N, h->in_state.as<double>(), h->in_target.as<double>(),
-                                          h->in_origin.as<double>(), d_thr, d_slow, h->loop_log.as<double>(),
-                                          h->loop_ticks.as<int>(), h->loop_status.as<int>());
+    int rc = held_loop_core(h, p, N, h->in_state.as<double>(), h->in_target.as<double>(), h->in_origin.as<double>(), d_thr,
+                            d_slow, d_events, n_events, radius_u_turn, h->loop_log.as<double>(), h->loop_ticks.as<int>(),
+                            h->loop_status.as<int>(), out_final ? h->loop_final.as<double>() : nullptr);
     if (rc) return rc;
+    if (out_final) CK(cudaMemcpyAsync(out_final, h->loop_final.p, sizeof(double) * 6 * N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_log, h->loop_log.p, sizeof(double) * nlog, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_ticks, h->loop_ticks.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_status, h->loop_status.p, sizeof(int) * N, cudaMemcpyDeviceToHost, st));

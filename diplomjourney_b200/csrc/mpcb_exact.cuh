@@ -10,37 +10,6 @@
 
 namespace mpcb {
 
-// round-to-nearest add / mul / sqrt that the compiler must not contract into FMAs (the reference evaluates
-// x + v*cos(phi)*dt as separate operations), and a read-only load
-MPCB_HD double dadd(double a, double b) {
-#ifdef __CUDA_ARCH__
-    return __dadd_rn(a, b);
-#else
-    return a + b;
-#endif
-}
-MPCB_HD double dmul(double a, double b) {
-#ifdef __CUDA_ARCH__
-    return __dmul_rn(a, b);
-#else
-    return a * b;
-#endif
-}
-MPCB_HD double dsqrt(double a) {
-#ifdef __CUDA_ARCH__
-    return __dsqrt_rn(a);
-#else
-    return std::sqrt(a);
-#endif
-}
-MPCB_HD double ro_load(const double *p) {
-#ifdef __CUDA_ARCH__
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
-
 // ---- float64 evaluation by the reference's own formula and operation order
 // (iteration_of_predict math_model.py:110-114, control_criterion :82-86 / tree :82-87)
 MPCB_HD void exact_step(const LaunchArgs &a, const double4 *tab, const double *vt,

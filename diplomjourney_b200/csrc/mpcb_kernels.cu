@@ -994,7 +994,6 @@ __device__ __forceinline__ bool tile_survives(const LaunchArgs &a, unsigned long
     const SolveParams &P = a.sp[n];
     cut_nodes = 0;
     if (P.flags & kFlagSkip) return false;
-    const unsigned long long S = (unsigned long long)a.g.S;
     const unsigned long long p_lo = a.u_begin + tile * kThreads;
     const unsigned long long p_hi = min(p_lo + (unsigned long long)kThreads, a.u_end);     // exclusive
     const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;

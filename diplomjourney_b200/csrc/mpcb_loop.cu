@@ -6,13 +6,15 @@
 //             solve     HELD predictive_control, slow-down override        math_model_tree.py:308-361
 //             apply     finishing heuristic m, result pose, threshold reset math_model_tree.py:388-429
 //             stop      is_on_target, repeated-position ("Recursive error") math_model_tree.py:48-52,559-563
-// The scripted operator events of the reference's demo run (ticks 60/90/110) are host logic and
-// are not part of this loop.
+//             events    new_target / turn_left / turn_right + slow_down     math_model_tree.py:118-226,564-569
+// Operator events come as a script {tick, kind, a, b} (the reference's demo: turn_right at tick 60, turn_left at 90,
+// new_target at 110); thread 0 applies an event after the tick it names, to the robot's own pose, and the CTA
+// reloads target, line and cost constants from shared memory.
 //
 // A HELD tick is tiny (S <= 451 candidates x H steps), so the loop is latency-bound, not
 // throughput-bound: everything is evaluated directly in float64 with the reference's formula and
 // operation order -- no fp32 stage, no refinement -- and the batch dimension (robots) fills the GPU.
-#include "mpcb_types.cuh"
+#include "mpcb_events.cuh"
 
 #include <cmath>
 
@@ -130,6 +132,7 @@ __device__ __forceinline__ void held_block_solve(const mpcb_loop_params &p, cons
 
 __device__ __forceinline__ void load_cost(LoopCost &cost, const double *target, const double *origin, long long n,
                                           int kind) {
+    // (also called with n = 0 on the CTA's shared copy {x_t, y_t}, {x_0, y_0} after an operator event)
     cost.xt = target[2 * n]; cost.yt = target[2 * n + 1];
     cost.ox = origin[2 * n]; cost.oy = origin[2 * n + 1];
     cost.A = cost.yt - cost.oy; cost.B = cost.xt - cost.ox;
@@ -148,8 +151,14 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
     // separate words: each is rewritten only after every thread has passed at least two CTA barriers since reading it.
     __shared__ int s_ctl[5];
     __shared__ double s_vslow;
+    // operator events: x_t, y_t, x_0, y_0 as thread 0 last set them, and how many events it has applied (a counter, not
+    // a flag: every thread compares it with its own copy after the tick's last barrier, so it never has to be cleared)
+    __shared__ double s_line[4];
+    __shared__ int s_events;
     const mpcb_loop_params &p = a.p;
     const int tid = threadIdx.x;
+    if (tid == 0) s_events = 0;
+    int seen_events = 0;
 
     for (long long n = blockIdx.x; n < a.N; n += gridDim.x) {
         LoopCost cost;
@@ -221,17 +230,36 @@ __global__ void __launch_bounds__(kLoopThreads) held_loop_kernel(const LoopArgs 
                     s_state[0] = rx; s_state[1] = ry; s_state[2] = rphi; s_state[3] = res_v; s_state[4] = res_beta;
                     ticks += 1;
                     if (recursive) { stop = 1; status = 1; }        // "Recursive error." (math_model_tree.py:559-561)
-                    else if (rx == xprev && ry == yprev) recursive = true;
+                    else {
+                        if (rx == xprev && ry == yprev) recursive = true;
+                        // operator events of this tick (math_model_tree.py:564-569), in script order
+                        bool fired = false;
+                        for (int e = 0; e < a.n_events; ++e)
+                            if (a.events[e].tick == ticks) {
+                                if (!fired) { s_line[0] = cost.xt; s_line[1] = cost.yt; s_line[2] = cost.ox; s_line[3] = cost.oy; }
+                                apply_event(a.events[e], a.radius_u_turn, rx, ry, rphi, s_line, slow_steps);
+                                fired = true;
+                            }
+                        if (fired) s_events += 1;
+                    }
                     xprev = rx; yprev = ry;
                 }
                 s_ctl[4] = stop;
             }
             __syncthreads();
             if (s_ctl[4]) break;
+            if (s_events != seen_events) {          // uniform: written before the barrier above
+                seen_events = s_events;
+                load_cost(cost, s_line, s_line + 2, 0, p.cost_kind);
+            }
         }
         if (tid == 0) {
             a.out_ticks[n] = ticks;
             a.out_status[n] = status;
+            if (a.out_final) {
+                double *f = a.out_final + 6 * n;
+                f[0] = cost.xt; f[1] = cost.yt; f[2] = cost.ox; f[3] = cost.oy; f[4] = (double)slow_steps; f[5] = (double)m;
+            }
         }
     }
 }

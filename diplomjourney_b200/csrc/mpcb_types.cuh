@@ -5,6 +5,7 @@
 //   SolveParams  one 256-byte record per MPC solve, built on the device by prep_kernel
 //   LaunchArgs   per launch, passed by value (constant bank)
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -32,6 +33,37 @@ constexpr double kWd = 10000.0;
 #define MPCB_HD inline
 #define MPCB_HD_NOINLINE inline
 #endif
+
+// round-to-nearest add / mul / sqrt that the compiler must not contract into FMAs (the reference evaluates
+// x + v*cos(phi)*dt as separate operations), and a read-only load
+MPCB_HD double dadd(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+MPCB_HD double dmul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+MPCB_HD double dsqrt(double a) {
+#ifdef __CUDA_ARCH__
+    return __dsqrt_rn(a);
+#else
+    return std::sqrt(a);
+#endif
+}
+MPCB_HD double ro_load(const double *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // Division of a 64-bit index by an invariant divisor (Granlund-Montgomery round-up form).  Host/device: the CPU
 // test-suite checks the very same code (tests/test_shipped_code_on_host.py).
@@ -198,6 +230,11 @@ struct LoopArgs {
     const int *slow_steps;
     double *out_log;
     int *out_ticks, *out_status;
+    // operator events applied between ticks (device copies; n_events = 0: none)
+    const mpcb_loop_event *events;
+    int n_events;
+    double radius_u_turn;
+    double *out_final;                                 // [N][6] x_t, y_t, x_0, y_0, steps_for_slowing, m; nullable
 };
 
 // one online tick of a batch of robots with per-robot acceleration windows (mpcb_loop.cu); all pointers are device

@@ -318,6 +318,11 @@ need_scatter = False
 scripted_events = True      # the demo run's operator events at ticks 1/60/90/110; set False for a plain run
 
 
+# the programmed run's script (math_model_tree.py:564-569) in the form mpcb_held_closed_loop_events takes
+DEMO_EVENTS = ((60, _native.EVENT_TURN_RIGHT, 2.0, 0.0), (90, _native.EVENT_TURN_LEFT, 2.0, 0.0),
+               (110, _native.EVENT_NEW_TARGET, 2.0, 3.0))
+
+
 def _scripted_events(tick, px, py, pphi, pv, isActual):
     """Operator events of the demo run (math_model_tree.py:564-569,617-624)."""
     if not scripted_events:
@@ -462,18 +467,22 @@ def _math_mpc_batch_ticks(ini, tgt, org, first, max_ticks, cost_kind, isActual, 
 
 
 def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origin=None, cost_kind=None,
-                   isActual=False, rngs=None, events=False):
+                   isActual=False, rngs=None, events=False, host_loop=False):
     """EXTENSION (not in the reference): the closed loop of ``math_mpc`` for a whole batch of robots.
     ``initial_coordinates`` [N][5] = x, y, phi, v, beta; ``target_coordinates`` [N][2].  The tracked line starts at
     the module's x_0, y_0 unless ``origin`` [N][2] is given.
 
-    * ``isActual=False, events=False``: executed on the GPU without returning to the host between ticks (one CTA
-      per robot, ``mpcb_held_closed_loop``).
+    * ``isActual=False``: executed on the GPU without returning to the host between ticks (one CTA per robot,
+      ``mpcb_held_closed_loop``).  ``events=True`` adds the demo run's scripted operator events (:564-569: turn_right
+      at tick 60, turn_left at 90, new_target(2, 3) at 110), ``events=[(tick, kind, a, b), ...]`` any other script
+      (``_native.EVENT_*``); they too are applied on the device, to each robot's own pose.  The dict then also carries
+      ``final[N][6]`` = x_t, y_t, x_0, y_0, steps_for_slowing, m.
     * ``isActual=True`` (actuator noise, math_model_tree.py:259-275,590-597; ``rngs`` = one numpy RandomState per
-      robot, default the module generator) and/or ``events=True`` (the demo run's scripted operator events,
-      :564-569,617-624): the host draws the noise and applies the events between ticks, and every tick is ONE batched
-      device solve with per-robot acceleration windows (``mpcb_solve_held_windows``).  The returned dict then also
-      carries ``robots``: per robot the state and log lists of the reference module (``actual_result_trajectory_x`` ...).
+      robot, default the module generator; ``events=True`` = the demo script, :617-624): the host draws the noise and
+      applies the events between ticks, and every tick is ONE batched device solve with per-robot acceleration windows
+      (``mpcb_solve_held_windows``).  The returned dict then also carries ``robots``: per robot the state and log
+      lists of the reference module (``actual_result_trajectory_x`` ...).  ``host_loop=True`` takes this per-tick
+      path for a noise-free run as well (events then = the demo script, applied by the module's own functions).
 
     Returns dict(log[N][max_ticks][5], ticks[N], status[N])."""
     from . import config as _cfg
@@ -493,11 +502,13 @@ def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origi
             first[i] = control_criterion([org[i, 0], org[i, 1], phi_0])
     finally:
         g.update(x_t=saved[0], y_t=saved[1], x_0=saved[2], y_0=saved[3])
-    if isActual or events:
-        return _math_mpc_batch_ticks(ini, tgt, org, first, max_ticks, cost_kind, isActual, rngs, events)
+    if isActual or host_loop:
+        return _math_mpc_batch_ticks(ini, tgt, org, first, max_ticks, cost_kind, isActual, rngs, bool(events))
     params = _native.LoopParams.from_config(_cfg, _native.COST_TREE if cost_kind is None else cost_kind,
                                             prediction_horizon, max_ticks)
-    return _solver().held_closed_loop(params, ini, tgt, org, first_threshold=first)
+    script = DEMO_EVENTS if events is True else list(events or ())
+    return _solver().held_closed_loop(params, ini, tgt, org, first_threshold=first, events=script or None,
+                                      radius_u_turn=radius_u_turn)
 
 
 def reset_state(g=None):

@@ -218,6 +218,30 @@ MPCB_API int mpcb_held_closed_loop_device(mpcb_handle *h, const mpcb_loop_params
                                  const double *first_threshold, const int32_t *slow_steps,
                                  double *out_log, int32_t *out_ticks, int32_t *out_status);
 
+/* The same loop WITH the operator events of the reference's run (math_model_tree.py:564-569: turn_right at tick 60,
+ * turn_left at 90, new_target at 110 in the demo) applied on the device between ticks: after the tick whose 1-based
+ * number equals `tick`, every running robot gets
+ *   MPCB_EVENT_NEW_TARGET  new_target(x, y, phi, a, b, v)     math_model_tree.py:118-129: target := (a, b), the tracked line
+ *                          restarts at the robot's pose, slow_down(30 deg) -> 10 slowed ticks
+ *   MPCB_EVENT_TURN_LEFT / _RIGHT  turn_left / turn_right(x, y, phi, distance = a, v)   :142-215: a synthetic target from
+ *                          the robot's pose, the U-turn radius L / sin(beta_max) (`radius_u_turn`) and the quadrant of
+ *                          phi, then new_target and slow_down(90 deg) -> 20 slowed ticks
+ * One script for the whole batch; its effect differs per robot because it starts from the robot's own pose.
+ *   out_final[N][6]  (nullable) x_t, y_t, x_0, y_0, steps_for_slowing, m when the robot stopped */
+typedef struct {
+    int32_t tick;   /* 1-based number of the tick after which the event fires */
+    int32_t kind;   /* MPCB_EVENT_* */
+    double a, b;
+} mpcb_loop_event;
+#define MPCB_EVENT_NEW_TARGET 1
+#define MPCB_EVENT_TURN_LEFT 2
+#define MPCB_EVENT_TURN_RIGHT 3
+MPCB_API int mpcb_held_closed_loop_events_host(mpcb_handle *h, const mpcb_loop_params *p, int64_t N,
+                                      const double *init, const double *target, const double *origin,
+                                      const double *first_threshold, const int32_t *slow_steps,
+                                      const mpcb_loop_event *events, int32_t n_events, double radius_u_turn,
+                                      double *out_log, int32_t *out_ticks, int32_t *out_status, double *out_final);
+
 /* ONE online tick for a batch of robots that each have their OWN acceleration window.  The
  * reference rebuilds the control window per robot and per tick around the robot's current (v, beta)
  * (vector_of_velocities / vector_of_beta_angles, math_model_tree.py:239-256, called at :543-545 and -- with the noisy

@@ -16,6 +16,7 @@ Fixtures:
                       operator events at ticks 60/90/110 and the slow-down override.
   held_single.json    single HELD predictive_control calls incl. slow flag.
   pieces.json         iteration_of_predict / control_criterion / grid generators.
+  operator_events.json  new_target / turn_left / turn_right / slow_down in every heading quadrant.
 """
 from __future__ import annotations
 
@@ -192,13 +193,42 @@ def gen_pieces():
                                        b_head=_f(Bd[:3]), b_tail=_f(Bd[-3:])))
 
 
+def gen_operator_events():
+    """new_target / turn_left / turn_right (+ slow_down) of math_model_tree.py:118-226 on poses in every heading
+    quadrant the functions distinguish (incl. phi < pi/2, phi > 2 pi and the quadrant borders)."""
+    T = R.load_tree()
+    rng = np.random.default_rng(17)
+    phis = list(rng.uniform(-1.0, 8.0, 44)) + [math.pi / 2, math.pi, 3 * math.pi / 2, 2 * math.pi]
+    cases = []
+    for i, phi in enumerate(phis):
+        x, y = (float(q) for q in rng.uniform(-4, 4, 2))
+        d = float(rng.uniform(0.5, 3.0))
+        for kind in ("turn_left", "turn_right", "new_target"):
+            T.steps_for_slowing = int(rng.integers(0, 30))
+            before = int(T.steps_for_slowing)
+            if kind == "new_target":
+                a, b = (float(q) for q in rng.uniform(-4, 4, 2))
+                T.new_target(x, y, float(phi), a, b, 0.4)
+            else:
+                a, b = d, 0.0
+                getattr(T, kind)(x, y, float(phi), d, 0.4)
+            cases.append(dict(kind=kind, pose=[x, y, float(phi)], a=a, b=b, slow_before=before,
+                              out=_f([T.x_t, T.y_t, T.x_0, T.y_0]), steps_for_slowing=int(T.steps_for_slowing)))
+    slow = [dict(deg=float(dg), before=7, after=None) for dg in (0, 5, 9.99, 10, 30, 45, 45.01, 90, 90.01, 180, -30, -95)]
+    for c in slow:
+        T.steps_for_slowing = c["before"]
+        T.slow_down(math.radians(c["deg"]))
+        c["after"] = int(T.steps_for_slowing)
+    return dict(meta=_meta(), radius_u_turn=float(T.radius_u_turn), cases=cases, slow_down=slow)
+
+
 def main():
     if not R.reference_available():
         raise SystemExit("needs /root/reference (build container only)")
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("pieces", gen_pieces), ("held_single", gen_held_single), ("held_short_loops", gen_held_short_loops),
-                     ("held_actual", gen_held_actual),
+                     ("held_actual", gen_held_actual), ("operator_events", gen_operator_events),
                      ("full_h3", gen_full), ("held_closed_loop", gen_held_closed_loop)):
         if only and name not in only:
             continue

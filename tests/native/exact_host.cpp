@@ -1,11 +1,21 @@
 // TEST HARNESS (not part of the product): compiles SHIPPED pieces of the CUDA library for the host with g++ --
 // csrc/mpcb_exact.cuh (the float64 leaf evaluation whose results the library returns) and the invariant-divisor
-// index decoding of csrc/mpcb_types.cuh -- so that tests/test_shipped_code_on_host.py can check them against the
+// index decoding of csrc/mpcb_types.cuh, and the operator events of csrc/mpcb_events.cuh -- so that tests/test_shipped_code_on_host.py can check them against the
 // reference's golden outputs and the oracle without a GPU.
 #include <cmath>
 #include <vector>
 
+#include "mpcb_events.cuh"
 #include "mpcb_exact.cuh"
+
+// one operator event (kind 1 new_target(a, b), 2 turn_left(a), 3 turn_right(a)) on a pose: line[4] = x_t, y_t, x_0, y_0
+extern "C" int mpcb_test_apply_event(int kind, double a, double b, double radius, double x, double y, double phi,
+                                     int slow_before, double *line) {
+    mpcb_loop_event e = {0, kind, a, b};
+    int slow = slow_before;
+    mpcb::apply_event(e, radius, x, y, phi, line, slow);
+    return slow;
+}
 
 extern "C" void mpcb_test_fastdiv64(unsigned long long d, long long count, const unsigned long long *n,
                                     unsigned long long *q) {

@@ -220,6 +220,42 @@ def test_actual_mode_batch_matches_reference_seeded_runs(golden):
     _actual_batch_equals_fixture_and_sequential(mt, golden)
 
 
+def test_device_closed_loop_with_operator_events(golden):
+    """mpcb_held_closed_loop_events: the reference's programmed run math_mpc([0,0,0,0,0], [2,3], False) -- 150 ticks with
+    turn_right at 60, turn_left at 90, new_target at 110 and the slow-down override after each -- executed in ONE
+    launch, events applied on the device, against the reference's own log; and a batch of robots that start elsewhere
+    against the per-tick path on which the module's own new_target / turn_* functions apply the events."""
+    nat, _ = _window_params()
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    mt._backend = None
+    log = golden("held_closed_loop")["log"]
+    rng = np.random.default_rng(5)
+    n = 24
+    init = np.zeros((n, 5)); init[1:, :2] = rng.uniform(-1, 1, (n - 1, 2)); init[1:, 2] = rng.uniform(-0.5, 7.0, n - 1)
+    tgt = np.tile([2.0, 3.0], (n, 1)); tgt[1:] += rng.uniform(-1, 1, (n - 1, 2))
+    r = mt.math_mpc_batch(init, tgt, max_ticks=200, events=True)
+    ref = np.array([log[k][1:] for k in ("result_trajectory_x", "result_trajectory_y", "result_trajectory_phi",
+                                         "result_trajectory_v", "result_trajectory_beta")], dtype=float).T
+    fin = log["final"]
+    assert r["ticks"][0] == ref.shape[0] == fin["p"] - 1 and r["status"][0] == nat.LOOP_ON_TARGET
+    np.testing.assert_allclose(r["log"][0, :ref.shape[0]], ref, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(r["final"][0], [2.0, 3.0, fin["x_0"], fin["y_0"], fin["steps_for_slowing"], fin["m"]],
+                               rtol=0, atol=1e-9)
+    host = mt.math_mpc_batch(init, tgt, max_ticks=200, events=True, host_loop=True)
+    np.testing.assert_array_equal(r["ticks"], host["ticks"])
+    np.testing.assert_array_equal(r["status"], host["status"])
+    np.testing.assert_allclose(r["log"], host["log"], rtol=0, atol=1e-9, equal_nan=True)
+    for i, c in enumerate(host["robots"]):
+        np.testing.assert_allclose(r["final"][i], [c["x_t"], c["y_t"], c["x_0"], c["y_0"], c["steps_for_slowing"], c["m"]],
+                                   rtol=0, atol=1e-9)
+    assert (r["ticks"] > 110).sum() >= 4 and len({int(q) for q in r["ticks"]}) > 3      # events really fired, runs differ
+    # a custom script: one new target after tick 5 == two event-free loops chained by hand
+    a = mt.math_mpc_batch(init[:1], tgt[:1], max_ticks=200, events=[(5, nat.EVENT_NEW_TARGET, -1.0, 1.5)])
+    assert a["final"][0, 0] == -1.0 and a["final"][0, 1] == 1.5 and a["ticks"][0] > 5
+    np.testing.assert_array_equal(a["final"][0, 2:4], a["log"][0, 4, :2])               # the line restarts at the pose of tick 5
+    np.testing.assert_array_equal(a["log"][0, :5], r["log"][0, :5])
+
+
 def test_device_closed_loop_many_robots_per_cta():
     """More robots than resident CTAs: every CTA runs several robots back to back (the stop flags of one robot's loop
     must not leak into the next).  4,096 robots == the same robots in batches of 64."""

@@ -44,6 +44,27 @@ def test_signatures_match_reference():
     assert mm.optimal_trajectory == [[[0]]] and rm.optimal_trajectory == [0]
 
 
+def test_operator_events_against_reference(golden):
+    """new_target / turn_left / turn_right / slow_down of the mirror module == the reference's (math_model_tree.py:118-226)
+    in every heading quadrant."""
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    g = golden("operator_events")
+    assert mt.radius_u_turn == g["radius_u_turn"]
+    for c in g["cases"]:
+        mt.steps_for_slowing = c["slow_before"]
+        if c["kind"] == "new_target":
+            mt.new_target(*c["pose"], c["a"], c["b"], 0.4)
+        else:
+            getattr(mt, c["kind"])(*c["pose"], c["a"], 0.4)
+        assert [mt.x_t, mt.y_t, mt.x_0, mt.y_0] == c["out"], c
+        assert mt.steps_for_slowing == c["steps_for_slowing"], c
+    for c in g["slow_down"]:
+        mt.steps_for_slowing = c["before"]
+        mt.slow_down(math.radians(c["deg"]))
+        assert mt.steps_for_slowing == c["after"], c
+    importlib.reload(mt)
+
+
 def test_scalar_helpers_against_reference(golden):
     mm = importlib.import_module("diplomjourney_b200.math_model")
     mt = importlib.import_module("diplomjourney_b200.math_model_tree")

@@ -36,6 +36,7 @@ def host():
                                          ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_longlong, dp,
                                          ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_double]
     lib.mpcb_test_exact_cost.restype = ctypes.c_double
+    lib.mpcb_test_apply_event.argtypes = [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int, dp]
     return lib
 
 
@@ -131,3 +132,17 @@ def test_exact_evaluation_matches_the_oracle_on_random_leaves(host, cost):
                 Jo = C.exact_leaf_cost(x[:3], x[3:5], x[:2], V, B, int(j), H, cost)
                 assert J == pytest.approx(Jo, rel=1e-12), (H, j)
                 assert fc == int(j) // S ** (H - 1)
+
+
+def test_operator_events_reproduce_the_reference(host, golden):
+    """apply_event of csrc/mpcb_exact.cuh -- what the device-resident closed loop executes between two ticks -- against
+    the reference's own new_target / turn_left / turn_right (+ slow_down) in every heading quadrant (bit-identical on
+    the host, where sin / cos are the libm the reference used)."""
+    g = golden("operator_events")
+    kinds = {"new_target": 1, "turn_left": 2, "turn_right": 3}
+    for c in g["cases"]:
+        line = np.full(4, np.nan)
+        slow = host.mpcb_test_apply_event(kinds[c["kind"]], c["a"], c["b"], g["radius_u_turn"], *c["pose"], c["slow_before"],
+                                          line.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        np.testing.assert_allclose(line, c["out"], rtol=0, atol=2e-15, err_msg=str(c))
+        assert slow == c["steps_for_slowing"], c
