@@ -31,6 +31,7 @@ cudaError_t launch_frontier_expand(cudaStream_t, const LaunchArgs &, int k, cons
                                    unsigned *overflow, int sms);
 cudaError_t launch_tilewalk_fallback(cudaStream_t, const LaunchArgs &, unsigned long long all_tiles, int sms);
 cudaError_t launch_cand_resolve(cudaStream_t, const LaunchArgs &, int sms);
+cudaError_t launch_refine_scan(cudaStream_t, const LaunchArgs &, int sms);
 cudaError_t launch_finalize(cudaStream_t, const LaunchArgs &, double *, long long *, double *, double *);
 cudaError_t launch_dump(cudaStream_t, const LaunchArgs &, bool prefix, double *jrel, int sms);
 cudaError_t launch_held_loop(cudaStream_t, const LoopArgs &, int sms);
@@ -126,9 +127,12 @@ void fill_args(mpcb_handle *h, LaunchArgs &a, int mode, int cost_kind, int H, lo
     a.N = N;
     unsigned long long S = (unsigned long long)h->g.S, pw = 1;
     a.idx32 = (!pl.prefix && pl.u_end < (1ULL << 32)) ? 1 : 0;
+    // prefix algorithm: units are depth-(H-1) nodes, decoded with fd[1..H-1]; 32-bit dividers when every node index fits
+    a.node32 = (pl.prefix && pl.u_end < (1ULL << 32)) ? 1 : 0;
     for (int k = H - 1; k >= 0; --k) {   // fd[k].d = S^(H-1-k)
         fastdiv_init(a.fd[k], pw);
-        if (a.idx32) fastdiv32_init(a.fd32[k], pw);
+        if ((a.idx32 || (a.node32 && k >= 1)) && pw < (1ULL << 32)) fastdiv32_init(a.fd32[k], pw);
+        else if (a.node32 && k >= 1) a.node32 = 0;
         if (mode == MPCB_MODE_FULL) pw *= S;
     }
     a.u_begin = pl.u_begin; a.u_end = pl.u_end;
@@ -278,7 +282,7 @@ int mpcb_destroy(mpcb_handle *h) {
                       &h->lock, &h->ub, &h->tile_list, &h->reduce_scratch, &h->in_state, &h->in_target, &h->in_origin, &h->in_thr, &h->in_flags, &h->out_cost,
                       &h->out_index, &h->out_traj, &h->out_ctl, &h->dump_rec, &h->dump_j, &h->loop_log, &h->loop_ticks,
                       &h->loop_status, &h->loop_events, &h->loop_final, &h->small_in, &h->small_out, &h->fl_last, &h->fl_k, &h->fl_have, &h->fl_flags,
-                      &h->fl_count, &h->nccl_scratch, &h->cand, &h->cand_J, &h->cand_sel})
+                      &h->fl_count, &h->nccl_scratch, &h->cand, &h->cand_J, &h->cand_sel, &h->node_list})
         b->release();
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -305,8 +309,13 @@ int mpcb_set_option(mpcb_handle *h, const char *name, double value) {
     else if (!strcmp(name, "small_path")) h->small_path = value != 0.0;
     else if (!strcmp(name, "zero_copy")) h->zero_copy = value != 0.0;
     else if (!strcmp(name, "candidate_list")) {
-        if (!(value >= 0.0 && value <= (double)(1u << 26))) return fail(h, MPCB_ERR_INVALID, "candidate_list out of range [0, 2^26]");
-        h->cand_cap = (unsigned)value;
+        if (value == -1.0) { h->cand_cap = 1u << 20; h->cand_auto = true; return MPCB_OK; }
+        if (!(value >= 0.0 && value <= (double)(1u << 26))) return fail(h, MPCB_ERR_INVALID, "candidate_list out of range [0, 2^26] (or -1)");
+        h->cand_cap = (unsigned)value; h->cand_auto = false;
+    }
+    else if (!strcmp(name, "node_list")) {
+        if (!(value >= 0.0 && value <= (double)(1u << 24))) return fail(h, MPCB_ERR_INVALID, "node_list out of range [0, 2^24]");
+        h->node_cap = (unsigned)value;
     }
     else if (!strcmp(name, "prune")) h->prune = value != 0.0;
     else if (!strcmp(name, "dump_direct")) h->dump_direct = value != 0.0;
@@ -398,19 +407,22 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     CK(h->sp.ensure(sizeof(SolveParams) * N));
     CK(h->segmin.ensure(sizeof(double) * std::max<unsigned long long>(a.total_segs, 1)));
     CK(h->worklist.ensure(sizeof(unsigned) * std::max<unsigned long long>(a.total_segs, 1)));
-    CK(h->misc.ensure(64));
+    CK(h->misc.ensure(128));
     CK(h->tau.ensure(sizeof(double) * N));
     CK(h->bestJ.ensure(sizeof(double) * N));
     CK(h->bestIdx.ensure(sizeof(long long) * N));
     CK(h->lock.ensure(sizeof(int) * N));
     CK(h->ub.ensure(sizeof(unsigned long long) * N));
     // misc: [0..3] work_count (u32) | [8..11] tile_count (u32, subtree cut) | [16..47] counters (4 x u64) |
-    //       [48..55] frontier counts (2 x u32) | [56..59] frontier overflow flag (u32) | [60..63] candidate count (u32)
+    //       [48..55] frontier counts (2 x u32) | [56..59] frontier overflow flag (u32) | [60..63] candidate count (u32) |
+    //       [4..7] listed refinement nodes (u32) | [64..71] next work item of the refinement filter (u64)
     unsigned *work_count = h->misc.as<unsigned>();
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 16);
-    CK(cudaMemsetAsync(h->misc.p, 0, 64, h->stream));
+    CK(cudaMemsetAsync(h->misc.p, 0, 128, h->stream));
     // candidate list of the refinement: [cand_cap] candidates + their float64 costs, per-solve key and index (all ones)
-    const unsigned cand_cap = h->cand_cap;
+    // (the prefix algorithm with a node list evaluates its in-window leaves where the scan finds them -- from the node's
+    //  float64 pose, one step each -- which beats listing them and three more launches; measured on cfg2 and cfg4)
+    const unsigned cand_cap = (h->cand_auto && pl.prefix && h->node_cap) ? 0u : h->cand_cap;
     if (cand_cap) {
         CK(h->cand.ensure(sizeof(Candidate) * cand_cap));
         CK(h->cand_J.ensure(sizeof(double) * cand_cap));
@@ -429,10 +441,15 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     a.counters = counters;
     a.tau = h->tau.as<double>();
     a.ub = h->ub.as<unsigned long long>();
+    a.refine_ctr = reinterpret_cast<unsigned long long *>(h->misc.as<char>() + 64);
     if (cand_cap) {
         a.cand = h->cand.as<Candidate>(); a.cand_count = h->misc.as<unsigned>() + 15; a.cand_cap = cand_cap;
         a.cand_J = h->cand_J.as<double>();
         a.cand_key = h->cand_sel.as<unsigned long long>(); a.cand_idx = a.cand_key + N;
+    }
+    if (pl.prefix && h->node_cap) {
+        CK(h->node_list.ensure(sizeof(RefineNode) * (size_t)h->node_cap));
+        a.node_list = h->node_list.as<RefineNode>(); a.node_count = h->misc.as<unsigned>() + 1; a.node_cap = h->node_cap;
     }
     a.prune = (pl.prefix && h->prune && H >= 2) ? 1 : 0;
     a.npt = h->npt;
@@ -514,6 +531,7 @@ static int solve_core(mpcb_handle *h, int mode, int cost_kind, int H, int64_t N,
     }
     if (a.total_segs > 0) {
         CK(launch_pass(h->stream, a, 2, pl.prefix, h->sms)); ++launches;
+        if (a.node_list) { CK(launch_refine_scan(h->stream, a, h->sms)); ++launches; }
         if (a.cand) { CK(launch_cand_resolve(h->stream, a, h->sms)); launches += 3; }
     }
     if (split_comm) {

@@ -13,12 +13,15 @@ namespace mpcb {
 using std::fabs; using std::fmin; using std::fmax; using std::sqrt; using std::fma;   // the float overloads too (host build)
 
 // cos / sin of the heading range reachable in i+1 steps, (i+1) dphi_max; cos = -2 marks "the whole circle"
+// (a.g.smax / smin / dphimax must be set: their float roundings for the fp32 pre-filter are taken here too)
 inline void bounds_set_heading_ranges(LaunchArgs &a, double dphimax) {
     for (int i = 0; i < kMaxH; ++i) {
         const double ang = (i + 1) * dphimax;
         a.cosk[i] = ang < 3.141592653589793 ? std::cos(ang) : -2.0;
         a.sink[i] = ang < 3.141592653589793 ? std::sin(ang) : 0.0;
     }
+    a.bc32[0] = (float)a.g.smax; a.bc32[1] = (float)a.g.smin; a.bc32[2] = (float)a.g.dphimax;
+    a.bc32[3] = (float)a.cosk[0]; a.bc32[4] = (float)a.sink[0];
 }
 
 // The scalars the bounds read, in the arithmetic type T they are evaluated in: double for the bounds that decide
@@ -150,11 +153,22 @@ struct Prefilter32 {
     float u0, w0, d0, e0, nx0, ny0, hp0;
 };
 
+// once per solve (prep_kernel): the start-frame quantities rounded to float
+MPCB_HD void prefilter_solve_consts(SolveParams &P) {
+    P.pf[0] = (float)P.u0; P.pf[1] = (float)P.w0; P.pf[2] = (float)P.d0; P.pf[3] = (float)P.e0;
+    P.pf[4] = (float)P.nx0; P.pf[5] = (float)P.ny0; P.pf[6] = (float)P.hp0;
+    P.pf[7] = (float)P.wl; P.pf[8] = (float)P.inv_wl; P.pf[9] = (float)P.wh;
+    P.pf[10] = 0.f; P.pf[11] = 0.f;
+}
+
+// per node: nothing but loads (the pre-filter runs on every node of a listed tile; conversions per node were a tenth of it)
 MPCB_HD Prefilter32 prefilter32(const LaunchArgs &a, const SolveParams &P) {
     Prefilter32 f;
-    f.k = bound_consts<float>(a, P, 1);
-    f.u0 = (float)P.u0; f.w0 = (float)P.w0; f.d0 = (float)P.d0; f.e0 = (float)P.e0;
-    f.nx0 = (float)P.nx0; f.ny0 = (float)P.ny0; f.hp0 = (float)P.hp0;
+    f.k.smax = a.bc32[0]; f.k.smin = a.bc32[1]; f.k.dphimax = a.bc32[2];
+    f.k.cosk[0] = a.bc32[3]; f.k.sink[0] = a.bc32[4];
+    f.u0 = P.pf[0]; f.w0 = P.pf[1]; f.d0 = P.pf[2]; f.e0 = P.pf[3];
+    f.nx0 = P.pf[4]; f.ny0 = P.pf[5]; f.hp0 = P.pf[6];
+    f.k.wl = P.pf[7]; f.k.inv_wl = P.pf[8]; f.k.wh = P.pf[9];
     return f;
 }
 

@@ -58,7 +58,10 @@ struct mpcb_handle_s {
     mpcb::DevBuf sp, segmin, worklist, misc, tau, bestJ, bestIdx, lock, ub, tile_list, reduce_scratch;
     mpcb::DevBuf in_state, in_target, in_origin, in_thr, in_flags, out_cost, out_index, out_traj, out_ctl, dump_rec, dump_j;
     mpcb::DevBuf cand, cand_J, cand_sel;  // refinement: listed candidates, their float64 costs, per-solve (key, index)
+    mpcb::DevBuf node_list;             // refinement: depth-(H-1) nodes whose leaves are to be scanned (RefineNode)
+    unsigned node_cap = 1u << 15;       // entries of that list (option "node_list"; 0 = scan where found)
     unsigned cand_cap = 1u << 20;       // entries of that list (option "candidate_list"; 0 = evaluate where found)
+    bool cand_auto = true;              // not set by the user: the prefix algorithm with a node list runs without it
     mpcb::DevBuf nccl_scratch;          // split tree: this rank's (cost, index) records + one slot per rank
     mpcb::DevBuf loop_log, loop_ticks, loop_status, loop_events, loop_final, small_in, small_out, fl_last, fl_k, fl_have, fl_flags, fl_count;
     void *pin_in = nullptr, *pin_out = nullptr;   // pinned staging of the low-latency path

@@ -196,15 +196,34 @@ struct NodeFrame {
     bool unmoved;              // the node has not moved at all (the reference's "on the line origin" special case)
 };
 
+// the controls i_0 .. i_{H-2} of depth-(H-1) node p, first step first: step(i) once per digit.  fd[k + 1].d = S^(H-2-k), so
+// the last digit is what is left (no division by 1), and indices below 2^32 take the 5-instruction 32-bit dividers
+template <typename F>
+__device__ __forceinline__ void node_digits(const LaunchArgs &a, unsigned long long p, F &&step) {
+    const int D = a.H - 1;
+    if (D <= 0) return;
+    if (a.node32) {
+        unsigned rem = (unsigned)p;
+        for (int k = 0; k + 1 < D; ++k) {
+            const unsigned i = a.fd32[k + 1].div(rem);
+            rem -= i * a.fd32[k + 1].d;
+            step(i);
+        }
+        step(rem);
+    } else {
+        unsigned long long rem = p;
+        for (int k = 0; k + 1 < D; ++k) {
+            const unsigned long long i = a.fd[k + 1].div(rem);
+            rem -= i * a.fd[k + 1].d;
+            step((unsigned)i);
+        }
+        step((unsigned)rem);
+    }
+}
+
 __device__ __forceinline__ void node_frame(const LaunchArgs &a, const SolveParams &P, unsigned long long p, NodeFrame &f) {
     double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
-    unsigned long long rem = p;
-    const int D = a.H - 1;
-    for (int k = 0; k < D; ++k) {
-        unsigned long long i = a.fd[k + 1].div(rem);
-        rem -= i * a.fd[k + 1].d;
-        walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
-    }
+    node_digits(a, p, [&](unsigned i) { walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp); });
     f.unmoved = (xi == 0.0 && eta == 0.0);
     const double relx = P.u0 - xi, rely = P.w0 - eta;
     f.u = cp * relx + sp * rely; f.w = cp * rely - sp * relx;
@@ -214,6 +233,18 @@ __device__ __forceinline__ void node_frame(const LaunchArgs &a, const SolveParam
     f.hp = P.hp0 - P.wh * psi;
     // J_rel is measured from the start pose's own cost terms: Kbase = kWd d0 + e0^2 + hp0^2
     f.base0 = kWd * (f.Dp - P.d0) + (f.ep - P.e0) * (f.ep + P.e0) + (f.hp - P.hp0) * (f.hp + P.hp0);
+}
+
+// fp32 pre-filter (mpcb_bounds.cuh): true = the float64 bound over the children of node p exceeds `bound` for certain
+// (the float bound from a float walk exceeds it by more than 8 tol1), so the node need not be set up in float64 at all
+__device__ __forceinline__ bool node_far32(const LaunchArgs &a, const SolveParams &P, unsigned long long p, double bound) {
+    const Prefilter32 pf = prefilter32(a, P);
+    float xi = 0.f, eta = 0.f, psi = 0.f, cp = 1.f, sp = 0.f;
+    node_digits(a, p, [&](unsigned i) {
+        const float4 t = __ldg(a.g.tab32 + i);
+        walk_step_t<float>(t.x, t.y, t.z, t.w, xi, eta, psi, cp, sp);
+    });
+    return node_prefilter32(pf, xi, eta, psi, cp, sp) > __double2float_ru(bound + 8.0 * P.tol1);
 }
 
 // no child can do better than: one step as straight at the target as the steering allows, the most favourable line offset
@@ -577,6 +608,9 @@ prefix_kernel(const LaunchArgs a) {
         qmode ? (unsigned long long)min(*a.q_count, a.q_cap) * qrounds
         : listed ? (unsigned long long)(*a.tile_count)
                  : PASS == 1 ? (unsigned long long)a.N * qps : (unsigned long long)(*a.work_count) * a.tps;
+    // nodes this warp cut (statistics): kept in a register and added to the global counter ONCE, after the loop -- one
+    // atomic per warp and tile on the same address (360k per cfg2 step) was what the pruned pass 1 waited for
+    unsigned long long cut_acc = 0;
     for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
         unsigned long long p_q = 0; bool in_q = false;                    // frontier mode: this thread's node
@@ -623,18 +657,9 @@ prefix_kernel(const LaunchArgs a) {
             unsigned pre_cut = 0;
             if (PASS == 1 && PRUNE && a.prefilter) {
                 bool far = false;
-                const Prefilter32 pf = prefilter32(a, P);          // per solve: uniform over the work item
                 if (active) {
-                    float xi = 0.f, eta = 0.f, psi = 0.f, cp = 1.f, sp = 0.f;
-                    unsigned long long rem = p;
-                    for (int k = 0; k + 1 < a.H; ++k) {
-                        const unsigned long long i = a.fd[k + 1].div(rem);
-                        rem -= i * a.fd[k + 1].d;
-                        const float4 t = __ldg(a.g.tab32 + i);
-                        walk_step_t<float>(t.x, t.y, t.z, t.w, xi, eta, psi, cp, sp);
-                    }
                     const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
-                    far = node_prefilter32(pf, xi, eta, psi, cp, sp) > __double2float_ru(bound + 8.0 * P.tol1);
+                    far = node_far32(a, P, p, bound);
                 }
                 pre_cut = __ballot_sync(0xffffffffu, far);
                 if (far) active = false;
@@ -646,7 +671,7 @@ prefix_kernel(const LaunchArgs a) {
                 const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
                 const bool cut = active && lb > bound;
                 const unsigned m = __ballot_sync(0xffffffffu, cut) | pre_cut;
-                if ((tid & 31) == 0 && m) atomicAdd(a.counters + 2, (unsigned long long)__popc(m));
+                cut_acc += (unsigned)__popc(m);
                 active = active && !cut;
             }
             // a warp none of whose nodes survived has nothing to score, publish or tighten (almost every warp of a listed
@@ -709,6 +734,7 @@ prefix_kernel(const LaunchArgs a) {
         if (qmode) publish_segmin_lanes(a, seg, segbest);
         else publish_segmin(a, seg, segbest);
     }
+    if (PASS == 1 && PRUNE && (tid & 31) == 0 && cut_acc) atomicAdd(a.counters + 2, cut_acc);
 }
 
 // ------------------------------------------------------------------------------------ prefix, pass 2 (refinement filter)
@@ -725,7 +751,10 @@ __device__ __forceinline__ void publish_best_warp(const LaunchArgs &a, long long
         const long long oj = __shfl_xor_sync(0xffffffffu, bj, o);
         lex_min(bJ, bj, oJ, oj);
     }
-    if ((threadIdx.x & 31) == 0 && bj >= 0) {
+    // (a result that costs more than the record already does cannot change it -- the record's cost only ever decreases --
+    //  so it does not queue for the lock: with one publish per listed node, thousands of warps took turns at the lock of
+    //  the same solve.  Equal costs go through: the lower index wins, and the pair is only read consistently under the lock.)
+    if ((threadIdx.x & 31) == 0 && bj >= 0 && !(bJ > *(volatile double *)(a.bestJ + n))) {
         while (atomicCAS(a.lock + n, 0, 1) != 0) {}
         __threadfence();
         double cJ = *(volatile double *)(a.bestJ + n);
@@ -736,6 +765,83 @@ __device__ __forceinline__ void publish_best_warp(const LaunchArgs &a, long long
         __threadfence();
         atomicExch(a.lock + n, 0);
     }
+}
+
+// float64 pose of depth-(H-1) node p by the reference's own steps: exactly what exact_cost computes on the way to any
+// leaf below it, so  exact_child_cost(pose, c) == exact_cost(p * S + c)  bit for bit (FULL trees)
+// (both out of line, like exact_cost: inlined, their double-precision sincos took the scan loop's registers)
+__device__ __noinline__ void exact_node_pose(const LaunchArgs &a, const SolveParams &P, unsigned long long p, double &x,
+                                             double &y, double &phi) {
+    const bool slow = (P.flags & kFlagSlow) != 0;
+    const double4 *tab = slow ? a.g.tab64_slow : a.g.tab64;
+    const double *vt = slow ? a.g.vtab_slow : a.g.vtab;
+    x = P.xs; y = P.ys; phi = P.phi0;
+    node_digits(a, p, [&](unsigned i) { exact_step(a, tab, vt, i, x, y, phi); });
+}
+__device__ __noinline__ double exact_child_cost(const LaunchArgs &a, const SolveParams &P, double x, double y, double phi,
+                                                unsigned c) {
+    const bool slow = (P.flags & kFlagSlow) != 0;
+    exact_step(a, slow ? a.g.tab64_slow : a.g.tab64, slow ? a.g.vtab_slow : a.g.vtab, c, x, y, phi);
+    return exact_terminal(a, P, x, y, phi);
+}
+
+// the S leaves of one node spread over the lanes of a warp: in-window leaves become candidates.  Those that do not fit
+// the candidate list are evaluated in float64 on the spot -- from the node's float64 pose, which the warp computes once
+// per node (H-1 of the H steps of every such leaf are the node's: a batch with tens of millions of in-window leaves, the
+// 16 x 16 grid at H = 4, spent three quarters of its refinement re-walking them)
+template <bool HEAD>
+__device__ __forceinline__ void scan_node(const LaunchArgs &a, const SolveParams &P, const float4 *__restrict__ tab, int S,
+                                          int lane, const ParentRegs &q, bool qnear, bool qspecial, float qLsp, float qthr,
+                                          double qbase, unsigned long long qp, long long n, double &bJ, long long &bj,
+                                          unsigned long long &cand_acc) {
+    bool have_pose = false;
+    double nx = 0.0, ny = 0.0, nphi = 0.0;
+    for (int c0 = 0; c0 < S; c0 += 32) {                       // uniform trip count: the warp votes inside
+        const int c = c0 + lane;
+        bool hit = false;
+        double jrel = 0.0;
+        if (c < S) {
+            const float4 t = tab[c];
+            float L = qnear ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, q) : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, q);
+            if (qspecial && t.z == 0.f) L = qLsp;
+            hit = L <= qthr;
+            jrel = qbase + (double)L;
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (!hm) continue;
+        cand_acc += hit ? 1u : 0u;
+        const long long j = (long long)(qp * (unsigned long long)S + (unsigned)c);
+        // list them: one reservation per warp, and none at all once the list is full (tens of millions of in-window
+        // leaves each taking a turn at the same counter were a third of the refinement of such a batch)
+        bool listed = false;
+        if (a.cand) {
+            unsigned slot0 = a.cand_cap;
+            if (lane == 0 && *(volatile unsigned *)a.cand_count < a.cand_cap) slot0 = atomicAdd(a.cand_count, (unsigned)__popc(hm));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            const unsigned slot = slot0 + (unsigned)__popc(hm & ((1u << lane) - 1u));
+            if (hit && slot0 < a.cand_cap && slot < a.cand_cap) {
+                Candidate cd;
+                cd.j = j; cd.jrel = jrel; cd.n = (int)n; cd.pad = 0;
+                a.cand[slot] = cd;
+                listed = true;
+            }
+        }
+        const bool need = hit && !listed;
+        if (!__any_sync(0xffffffffu, need)) continue;
+        if (a.refine && a.mode != 1 && !have_pose) { exact_node_pose(a, P, qp, nx, ny, nphi); have_pose = true; }
+        if (need) {
+            const double J = !a.refine ? P.Kbase + jrel
+                             : a.mode != 1 ? exact_child_cost(a, P, nx, ny, nphi, (unsigned)c) : exact_cost(a, P, j, nullptr, nullptr);
+            lex_min(bJ, bj, J, j);
+        }
+    }
+}
+
+// the candidates a warp counted, added to the statistics once per warp
+__device__ __forceinline__ void flush_cand_count(const LaunchArgs &a, unsigned long long cand_acc) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand_acc += __shfl_xor_sync(0xffffffffu, cand_acc, o);
+    if ((threadIdx.x & 31) == 0 && cand_acc) atomicAdd(a.counters + 1, cand_acc);
 }
 
 template <bool HEAD>
@@ -752,19 +858,30 @@ __global__ void __launch_bounds__(kThreads, 4) refine_prefix_kernel(const Launch
     const float4 *__restrict__ tab = single ? s_leaf : a.g.leaf32;
     constexpr unsigned wpt = kThreads / 32;                                  // 32-node slices per tile
     const unsigned long long nww = (unsigned long long)(*a.work_count) * a.tps * wpt;
-    const unsigned long long gw = (unsigned long long)blockIdx.x * wpt + (tid >> 5);
-    const unsigned long long GW = (unsigned long long)gridDim.x * wpt;
-    for (unsigned long long ww = gw; ww < nww; ww += GW) {
+    unsigned long long seg_acc = 0;          // refined segments (statistics), added to the global counter once per warp
+    unsigned long long cand_acc = 0;         // in-window leaves (statistics), likewise
+    // Work items are handed out by a counter, not by position: what a slice costs ranges from nothing (no live node) to
+    // thousands of float64 evaluations, and with a fixed assignment a batch rich in in-window leaves ran on 5 warps per SM
+    // (warps active 8.5 %) while the others had long finished.
+    for (;;) {
+        unsigned long long ww = 0;
+        if (lane == 0) ww = atomicAdd(a.refine_ctr, 1ULL);
+        ww = __shfl_sync(0xffffffffu, ww, 0);
+        if (ww >= nww) break;
         const unsigned long long wt = ww / wpt;
         const unsigned sub = (unsigned)(ww - wt * wpt);
         unsigned seg; long long n; unsigned long long tile_lo, tile_hi;
         decode_work<2>(a, wt, seg, n, tile_lo, tile_hi);
-        if (lane == 0 && sub == 0 && (a.tps == 1 || wt % a.tps == 0)) atomicAdd(a.counters, 1ULL);
+        if (sub == 0 && (a.tps == 1 || wt % a.tps == 0)) seg_acc += 1;
         const SolveParams &P = a.sp[n];
         if (P.flags & kFlagSkip) continue;
         const double tau = a.tau[n];
         const unsigned long long p = a.u_begin + tile_lo * kThreads + sub * 32u + lane;
         bool active = tile_lo < tile_hi && p < a.u_end;
+        // (the same fp32 pre-filter as in the pruned pass 1, against this pass's bound: it drops only nodes the float64
+        //  test below drops as well)
+        if (active && a.prefilter && node_far32(a, P, p, tau + P.tol)) active = false;
+        if (!__any_sync(0xffffffffu, active)) continue;
         NodeFrame f;
         if (active) {
             node_frame(a, P, p, f);
@@ -779,6 +896,37 @@ __global__ void __launch_bounds__(kThreads, 4) refine_prefix_kernel(const Launch
         const bool special = active && (P.flags & kFlagStartIsOrigin) && f.unmoved;
         const float thr = __double2float_ru(tau - base);
         const float Lspecial = (float)(P.special - 0.25 * (double)pr.e2 * (double)pr.e2);
+        // The live nodes of a tile sit next to each other (a few steering angles of one speed), i.e. in one or two of
+        // its eight slices: scanned where they are found, those warps were the whole kernel (SM active cycles min / avg /
+        // max 87k / 192k / 319k).  They are listed instead and refine_scan_kernel spreads them over all warps.
+        // The list is kept short (option node_list, default 2^15): a solve batch with more live nodes than that has enough
+        // of them everywhere to keep every warp busy, and once the list is full (one plain load) nothing is reserved.
+        // Nor is anything listed once the candidate list has run full: a batch with that many in-window leaves evaluates
+        // them where they are found, and its nodes are no longer scarce.
+        int use_list = 0;
+        if (a.node_list) {                       // lane 0 decides for the warp (the branch below contains shuffles)
+            if (lane == 0)
+                use_list = *(volatile unsigned *)a.node_count < a.node_cap &&
+                           !(a.cand && *(volatile unsigned *)a.cand_count >= a.cand_cap);
+            use_list = __shfl_sync(0xffffffffu, use_list, 0);
+        }
+        if (use_list) {
+            const unsigned cnt = (unsigned)__popc(todo);
+            unsigned slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(a.node_count, cnt);
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            const unsigned slot = slot0 + (unsigned)__popc(todo & ((1u << lane) - 1u));
+            const bool fits = slot0 + cnt <= a.node_cap;                     // uniform
+            if (active && slot < a.node_cap) {
+                RefineNode e;
+                e.u = pr.u; e.w = pr.w; e.u2 = pr.u2; e.w2 = pr.w2; e.D2 = pr.D2; e.Dp = pr.Dp; e.nu = pr.nu; e.nw = pr.nw;
+                e.e2 = pr.e2; e.h2 = pr.h2; e.thr = thr; e.Lspecial = Lspecial; e.base = base; e.p = p;
+                e.n = fits ? (int)n : -1;                                    // overflow: reserved slots stay empty
+                e.flags = (near ? 1u : 0u) | (special ? 2u : 0u);
+                a.node_list[slot] = e;
+            }
+            if (fits) continue;
+        }
         double bJ = INFINITY; long long bj = -1;
         for (; todo; todo &= todo - 1) {
             const int src = __ffs(todo) - 1;
@@ -793,16 +941,52 @@ __global__ void __launch_bounds__(kThreads, 4) refine_prefix_kernel(const Launch
             const float qLsp = __shfl_sync(0xffffffffu, Lspecial, src), qthr = __shfl_sync(0xffffffffu, thr, src);
             const double qbase = __shfl_sync(0xffffffffu, base, src);
             const unsigned long long qp = __shfl_sync(0xffffffffu, p, src);
-            for (int c = lane; c < S; c += 32) {
-                const float4 t = tab[c];
-                float L = qnear ? leaf_val<HEAD, true>(t.x, t.y, t.z, t.w, q) : leaf_val<HEAD, false>(t.x, t.y, t.z, t.w, q);
-                if (qspecial && t.z == 0.f) L = qLsp;
-                if (L <= qthr)
-                    take_candidate(a, P, n, (long long)(qp * (unsigned long long)S + c), qbase + (double)L, bJ, bj);
-            }
+            scan_node<HEAD>(a, P, tab, S, lane, q, qnear, qspecial, qLsp, qthr, qbase, qp, n, bJ, bj, cand_acc);
         }
         if (__any_sync(0xffffffffu, bj >= 0)) publish_best_warp(a, n, bJ, bj);
     }
+    if (lane == 0 && seg_acc) atomicAdd(a.counters, seg_acc);
+    flush_cand_count(a, cand_acc);
+}
+
+// The listed nodes, one warp each (all scans cost the same: S leaves over 32 lanes).
+template <bool HEAD>
+__global__ void __launch_bounds__(kThreads, 4) refine_scan_kernel(const LaunchArgs a) {
+    extern __shared__ float4 s_leaf[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int S = a.g.S;
+    const bool single = S <= kLeafChunk;
+    const unsigned count = min(*a.node_count, a.node_cap);
+    if (count == 0) return;
+    if (single) {
+        for (int i = tid; i < S; i += blockDim.x) s_leaf[i] = __ldg(a.g.leaf32 + i);
+        __syncthreads();
+    }
+    const float4 *__restrict__ tab = single ? s_leaf : a.g.leaf32;
+    // every warp takes a contiguous run of the list (the filter appends the live nodes of a slice together, so a run is
+    // mostly one solve) and carries its best across the nodes of a solve: one publish per solve and warp, not per node
+    constexpr unsigned wpc = kThreads / 32;
+    const unsigned warps = gridDim.x * wpc, wid = blockIdx.x * wpc + (tid >> 5);
+    const unsigned per = (count + warps - 1) / warps;
+    const unsigned i0 = min(count, wid * per), i1 = min(count, i0 + per);
+    unsigned long long cand_acc = 0;
+    long long cur_n = -1;
+    double bJ = INFINITY; long long bj = -1;
+    for (unsigned i = i0; i < i1; ++i) {
+        const RefineNode e = a.node_list[i];                                 // the same entry on every lane
+        if (e.n < 0) continue;
+        if (e.n != cur_n) {
+            if (__any_sync(0xffffffffu, bj >= 0)) publish_best_warp(a, cur_n, bJ, bj);
+            cur_n = e.n; bJ = INFINITY; bj = -1;
+        }
+        ParentRegs q = {};
+        q.u = e.u; q.w = e.w; q.u2 = e.u2; q.w2 = e.w2; q.D2 = e.D2; q.Dp = e.Dp; q.nu = e.nu; q.nw = e.nw;
+        q.e2 = e.e2; q.h2 = e.h2;
+        scan_node<HEAD>(a, a.sp[e.n], tab, S, lane, q, (e.flags & 1u) != 0, (e.flags & 2u) != 0, e.Lspecial, e.thr, e.base,
+                        e.p, e.n, bJ, bj, cand_acc);
+    }
+    if (__any_sync(0xffffffffu, bj >= 0)) publish_best_warp(a, cur_n, bJ, bj);
+    flush_cand_count(a, cand_acc);
 }
 
 // ------------------------------------------------------------------------------------ prefix, several nodes per thread
@@ -1057,6 +1241,7 @@ __global__ void __launch_bounds__(kThreads, 4) tilewalk_fallback_kernel(const La
     }
     if (blockIdx.x == 0 && tid == 0) a.counters[3] = 0;          // what the abandoned descent had counted as cut
     const unsigned long long items = (all_tiles + kThreads - 1) / kThreads;
+    unsigned long long cut_acc = 0;          // nodes cut (statistics): lane 0's copy goes to the global counter after the loop
     for (unsigned long long w = blockIdx.x; w < items; w += gridDim.x) {
         const unsigned long long g = w * kThreads + tid;
         unsigned cut_nodes = 0;
@@ -1065,7 +1250,7 @@ __global__ void __launch_bounds__(kThreads, 4) tilewalk_fallback_kernel(const La
         __syncthreads();                                          // the previous item's list has been consumed
         if (lane == 0) s_warp[warp] = __popc(mk);
         for (int o = 16; o > 0; o >>= 1) cut_nodes += __shfl_xor_sync(0xffffffffu, cut_nodes, o);
-        if (lane == 0 && cut_nodes) atomicAdd(a.counters + 2, (unsigned long long)cut_nodes);
+        cut_acc += cut_nodes;
         __syncthreads();
         unsigned before = 0, total = 0;
         for (unsigned i = 0; i < kThreads / 32; ++i) { if (i < warp) before += s_warp[i]; total += s_warp[i]; }
@@ -1086,7 +1271,7 @@ __global__ void __launch_bounds__(kThreads, 4) tilewalk_fallback_kernel(const La
             const double bound = ordered_value(*(volatile unsigned long long *)(a.ub + n)) + P.tol1 + P.tol;
             const bool cut = active && lb > bound;
             const unsigned mc = __ballot_sync(0xffffffffu, cut);
-            if (lane == 0 && mc) atomicAdd(a.counters + 2, (unsigned long long)__popc(mc));
+            cut_acc += (unsigned)__popc(mc);
             active = active && !cut;
             const bool special = active && (P.flags & kFlagStartIsOrigin) && unmoved;
             if (!(near || special)) base = base_direct;
@@ -1111,6 +1296,7 @@ __global__ void __launch_bounds__(kThreads, 4) tilewalk_fallback_kernel(const La
             publish_segmin(a, seg, v);
         }
     }
+    if (lane == 0 && cut_acc) atomicAdd(a.counters + 2, cut_acc);
 }
 
 // ------------------------------------------------------------------------------------ prefix, pruned (pass 1)
@@ -1176,6 +1362,7 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
                                             : (unsigned long long)a.N * wtps;
     const unsigned long long gw = (unsigned long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const unsigned long long GW = (unsigned long long)gridDim.x * (kThreads / 32);
+    unsigned long long cut_acc = 0;          // nodes cut (statistics): one atomic per warp after the loop, not one per step
     for (unsigned long long ww = gw; ww < nww; ww += GW) {
         long long n; unsigned long long wt = 0, p_q = 0; bool in_q = false;
         if (qmode) {
@@ -1208,7 +1395,7 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
         const bool cut = in_range && lb > bound;
         const bool keep = in_range && !cut;
         const unsigned mk = __ballot_sync(0xffffffffu, keep), mc = __ballot_sync(0xffffffffu, cut);
-        if (lane == 0 && mc) atomicAdd(a.counters + 2, (unsigned long long)__popc(mc));
+        cut_acc += (unsigned)__popc(mc);
         if (keep) {
             QEntry e;
             e.pr = pr;
@@ -1224,6 +1411,7 @@ __global__ void __launch_bounds__(kThreads, 4) prefix_pruned_kernel(const Launch
         if (count >= 32) drain(32);
     }
     if (count > 0) drain(count);
+    if (lane == 0 && cut_acc) atomicAdd(a.counters + 2, cut_acc);
 }
 
 // ------------------------------------------------------------------------------------ leafwalk
@@ -1555,6 +1743,7 @@ __global__ void prep_kernel(long long N, const double *__restrict__ state, const
         P.tol1 = 2.0 * M1 * 1.1920928955078125e-07 * tol_scale;
     }
     P.flags = f; P.pad = 0;
+    prefilter_solve_consts(P);
     out[n] = P;
 }
 
@@ -1913,6 +2102,12 @@ cudaError_t launch_reduce_compact_wide(cudaStream_t st, const LaunchArgs &a, dou
     seg_compact_kernel<<<grid, kThreads, 0, st>>>(a, tau1, worklist, work_count);
     *launches += 3;
     return cudaGetLastError();
+}
+
+cudaError_t launch_refine_scan(cudaStream_t st, const LaunchArgs &a, int sms) {
+    const size_t sm2 = sizeof(float4) * (size_t)(a.g.S <= kLeafChunk ? a.g.S : 0);
+    return a.cost_kind == 0 ? launch_persistent(refine_scan_kernel<true>, a, 2, sm2, sms, st)
+                            : launch_persistent(refine_scan_kernel<false>, a, 2, sm2, sms, st);
 }
 
 cudaError_t launch_cand_resolve(cudaStream_t st, const LaunchArgs &a, int sms) {

@@ -2,7 +2,7 @@
 //
 // Everything a kernel needs lives in three places:
 //   GridTables   per control grid, built once by mpcb_set_grid (read-only, L2/L1 resident)
-//   SolveParams  one 256-byte record per MPC solve, built on the device by prep_kernel
+//   SolveParams  one 272-byte record per MPC solve, built on the device by prep_kernel
 //   LaunchArgs   per launch, passed by value (constant bank)
 #pragma once
 #include <cmath>
@@ -159,6 +159,9 @@ struct __align__(16) SolveParams {
     double special;             // 1e6 * wl^2: squared line term of the "on the origin" special case
     int flags;                  // bit0 slow, bit1 start_is_origin, bit2 near (leafwalk regime)
     int pad;
+    // the start-frame quantities rounded to float once per solve, for the fp32 pre-filter of the pruned passes
+    // (mpcb_bounds.cuh: prefilter_solve_consts / prefilter32): u0, w0, d0, e0, nx0, ny0, hp0, wl, 1/wl, wh
+    float pf[12];
 };
 constexpr int kFlagSlow = 1, kFlagStartIsOrigin = 2, kFlagNear = 4, kFlagSkip = 8;
 
@@ -166,13 +169,25 @@ constexpr int kFlagSlow = 1, kFlagStartIsOrigin = 2, kFlagNear = 4, kFlagSkip = 
 // cand_eval_kernel evaluates them one thread each)
 struct __align__(8) Candidate { long long j; double jrel; int n; int pad; };
 
+// refinement: a depth-(H-1) node whose bound reaches into the window, with the fp32 registers its leaves are scored
+// from (refine_prefix_kernel lists them, refine_scan_kernel scans each with one warp)
+struct __align__(16) RefineNode {
+    float u, w, u2, w2, D2, Dp, nu, nw, e2, h2;   // ParentRegs of the form pass 2 filters with
+    float thr, Lspecial;                          // window edge relative to the node, value of the special-case leaves
+    double base;
+    unsigned long long p;                         // node index
+    int n;                                        // solve; -1 = slot reserved but not filled (list overflow)
+    unsigned flags;                               // bit0 near, bit1 special
+};
+
 struct LaunchArgs {
     GridTables g;
     const SolveParams *sp;
     FastDiv64 fd[kMaxH];        // fd[k].d = S^(H-1-k)
-    FastDiv32 fd32[kMaxH];      // same divisors, valid when idx32 != 0 (every index and divisor < 2^32)
+    FastDiv32 fd32[kMaxH];      // same divisors, valid when idx32 != 0 (every index and divisor < 2^32); [1..] also when node32 != 0
     FastDiv64 fd_tiles, fd_S;   // division by tiles_per_solve and by S (the pruned kernels decode a global tile number per tile)
     int idx32;
+    int node32;                 // prefix algorithm: every depth-(H-1) node index < 2^32 -> node_digits decodes with fd32
     unsigned step_digits[kMaxH]; // base-S digits of kThreads (most significant first): leafwalk advances a leaf index by kThreads
     int lw_smem;                // leafwalk FULL: stage ctl32 in shared memory (S <= 4096)
     unsigned tile_units;        // units per tile: kThreads (prefix) or kThreads*kLeafPerThread (leafwalk)
@@ -193,6 +208,7 @@ struct LaunchArgs {
     int prune;
     int prefilter;                         // pruned pass 1: fp32 pre-filter of the node bound (mpcb_bounds.cuh)
     int screen;                            // exhaustive prefix pass 1: 0 = MUFU.SQRT per leaf, 1 = screened (sqrt only on nodes that can matter)
+    float bc32[5];                         // smax, smin, dphimax, cosk[0], sink[0] rounded to float (fp32 pre-filter)
     double cosk[kMaxH], sink[kMaxH];       // cos / sin of (i+1) dphi_max: the heading range reachable in i+1 steps (cos = -2: the whole circle)
     // subtree cut (pruned pass 1, H >= 3): tiles that survived the depth-(H-2) bound, as global tile numbers
     // n * tiles_per_solve + tile; null = walk every tile
@@ -210,6 +226,8 @@ struct LaunchArgs {
     int i0_begin, i0_end;                   // first-control range of this launch (probe)
     const double *tau;                     // [N] J_rel window upper edge
     // candidate list of the refinement (null: every candidate is evaluated where it is found)
+    unsigned long long *refine_ctr;        // next work item of the refinement filter (handed out dynamically)
+    RefineNode *node_list; unsigned *node_count; unsigned node_cap;    // null / 0: nodes are scanned where they are found
     Candidate *cand; unsigned *cand_count; unsigned cand_cap;
     double *cand_J;                        // [cand_cap] float64 cost of each listed candidate
     unsigned long long *cand_key;          // [N] ordered key of the smallest listed cost per solve

@@ -112,9 +112,16 @@ MPCB_API int mpcb_set_grid(mpcb_handle *h, const double *v, int nv, const double
  * "prefilter" (1, default; identical results: in the pruned pass 1 a node's bound is first evaluated in fp32 from an fp32
  * walk and the node dropped if that exceeds the upper bound by a margin of 8 error bounds -- which the float64 test would
  * do as well -- so that the float64 set-up is only paid by nodes near the bound; 0 = float64 test for every node),
- * "candidate_list" (entries, default 2^20; identical results: the refinement pass lists the leaves whose fp32 value lies
- * inside the error window and a second kernel evaluates them in float64 one thread each; candidates beyond the capacity
- * -- or all of them with 0 -- are evaluated by the thread that found them),
+ * "candidate_list" (entries; identical results: the refinement pass lists the leaves whose fp32 value lies inside the
+ * error window and a second kernel evaluates them in float64 one thread each; candidates beyond the capacity -- or all of
+ * them with 0 -- are evaluated by the thread that found them.  Default -1 = automatic: 2^20 for the leafwalk algorithm,
+ * none for the prefix algorithm while it has a "node_list", whose scan evaluates an in-window leaf from its node's
+ * float64 pose with one step),
+ * "node_list" (entries, default 2^15; identical results: the refinement pass first lists the depth-(H-1) nodes whose
+ * bound reaches into the error window and a second kernel scans the leaves of each listed node with one warp, so that
+ * a few thousand scans are spread evenly over the GPU instead of staying with the few warps that found the nodes;
+ * nodes beyond the capacity -- or all of them with 0 -- are scanned where they are found, which is as good when there
+ * are many),
  * "nodes_per_thread" (1, 2 or 4, default 2: depth-(H-1) nodes each thread of the exhaustive prefix pass 1 holds --
  * identical results), "dump_direct" (diagnostics: mpcb_dump_leaves_host returns the cheaper fp32 form pass 1 ranks
  * with instead of the one pass 2 filters with; default 0), "frontier_cap" (see "subtree_cut"). */

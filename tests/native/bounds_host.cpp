@@ -27,6 +27,7 @@ extern "C" void mpcb_test_prefilter32(double smax, double smin, double dphimax, 
     mpcb::SolveParams P = {};
     P.u0 = solve[0]; P.w0 = solve[1]; P.d0 = solve[2]; P.e0 = solve[3]; P.nx0 = solve[4]; P.ny0 = solve[5];
     P.hp0 = solve[6]; P.wl = solve[7]; P.wh = solve[8]; P.inv_wl = 1.0 / P.wl;
+    mpcb::prefilter_solve_consts(P);                      // what prep_kernel does once per solve
     const mpcb::Prefilter32 f = mpcb::prefilter32(a, P);
     for (long long i = 0; i < n; ++i)
         out[i] = mpcb::node_prefilter32(f, (float)xi[i], (float)eta[i], (float)psi[i], std::cos((float)psi[i]),

@@ -551,7 +551,38 @@ def test_candidate_list_sizes_give_identical_records(solver, algo):
             for i, s_ in enumerate(sc):
                 _check(res[0], i, K.solve_full(s_[:3], s_[3:], s_[:2], V, B, 3, C.COST_MM), 3)
     finally:
-        solver.set_option("candidate_list", 1 << 20)
+        solver.set_option("candidate_list", -1)
+        solver.set_option("prune", 1)
+        solver.set_option("algo", nat.ALGO_AUTO)
+
+
+def test_node_list_sizes_give_identical_records(solver):
+    """option node_list (prefix algorithm): the refinement pass lists the nodes whose bound reaches into the window and a
+    second kernel scans each with one warp; with a list that is too small (3 entries: a warp whose nodes do not fit scans
+    them itself and leaves its reserved slots empty) and with 0 (every node scanned where it is found) the records, the
+    number of refined segments and the number of candidates are the same -- exhaustive and pruned, many exact ties."""
+    V, B = np.linspace(0.0, 1.0, 9), np.linspace(-1.0, 1.0, 11)
+    solver.set_grid(V, B, L, DT, VMIN)
+    sc = C.random_scenarios(12, 78)
+    sc[1, 3:5] = sc[1, :2] + [0.0, 1e-3]                        # the optimum stands still: thousands of tied candidates
+    solver.set_option("algo", nat.ALGO_PREFIX)
+    try:
+        for prune in (0, 1):
+            solver.set_option("prune", prune)
+            res, stats = [], []
+            for cap in (1 << 15, 3, 0):
+                solver.set_option("node_list", cap)
+                res.append(solver.solve(nat.MODE_FULL, nat.COST_MM, 3, sc[:, :3], sc[:, 3:5], sc[:, :2]))
+                st = solver.stats()
+                stats.append((st["refine_segments"], st["refine_candidates"]))
+            assert stats[0] == stats[1] == stats[2] and stats[0][1] >= len(sc), stats
+            for r in res[1:]:
+                for k in ("index", "cost", "traj", "first_control"):
+                    np.testing.assert_array_equal(r[k], res[0][k])
+            for i, s_ in enumerate(sc):
+                _check(res[0], i, K.solve_full(s_[:3], s_[3:], s_[:2], V, B, 3, C.COST_MM), 3)
+    finally:
+        solver.set_option("node_list", 1 << 15)
         solver.set_option("prune", 1)
         solver.set_option("algo", nat.ALGO_AUTO)
 

@@ -14,8 +14,8 @@ for name, V, B, H, n, seed in (("cfg2", np.array(C.vector_of_velocities(0.5)), n
     st, tg, og = (torch.from_numpy(np.ascontiguousarray(sc[:, a:b])).to(dev) for a, b in ((0, 3), (3, 5), (0, 2)))
     oc = torch.empty(n, dtype=torch.float64, device=dev); oi = torch.empty(n, dtype=torch.int64, device=dev)
     ref = None
-    for opts in ({"prefilter": 0}, {"prefilter": 1}, {"prefilter": 1, "candidate_list": 0}):
-        s.set_option("prune", 1); s.set_option("prefilter", 1); s.set_option("candidate_list", 1 << 20)
+    for opts in ({"prefilter": 0}, {"node_list": 0}, {}, {"candidate_list": 1 << 20}):
+        s.set_option("prune", 1); s.set_option("prefilter", 1); s.set_option("candidate_list", -1); s.set_option("node_list", 1 << 15)
         for k, v in opts.items():
             s.set_option(k, v)
         def step():
@@ -34,4 +34,4 @@ for name, V, B, H, n, seed in (("cfg2", np.array(C.vector_of_velocities(0.5)), n
         same = ref is None or (np.array_equal(cur[0], ref[0]) and np.array_equal(cur[1], ref[1]))
         ref = ref or cur
         stt = s.stats()
-        print(f"{name} {opts}: {e0.elapsed_time(e1) / 10:.3f} ms per {n} solves, pruned {stt['pruned_units']}/{stt['units'] * n}, launches {stt['kernel_launches']}, same={same}", flush=True)
+        print(f"{name} {opts}: {e0.elapsed_time(e1) / 10:.3f} ms per {n} solves, pruned {stt['pruned_units']}/{stt['units'] * n}, launches {stt['kernel_launches']}, refine segments {stt['refine_segments']} candidates {stt['refine_candidates']}, same={same}", flush=True)
