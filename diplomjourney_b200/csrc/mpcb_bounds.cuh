@@ -21,7 +21,7 @@ inline void bounds_set_heading_ranges(LaunchArgs &a, double dphimax) {
         a.sink[i] = ang < 3.141592653589793 ? std::sin(ang) : 0.0;
     }
     a.bc32[0] = (float)a.g.smax; a.bc32[1] = (float)a.g.smin; a.bc32[2] = (float)a.g.dphimax;
-    a.bc32[3] = (float)a.cosk[0]; a.bc32[4] = (float)a.sink[0];
+    a.bc32[3] = (float)a.cosk[0]; a.bc32[4] = (float)a.sink[0]; a.bc32[5] = (float)a.cosk[1]; a.bc32[6] = (float)a.sink[1];
 }
 
 // The scalars the bounds read, in the arithmetic type T they are evaluated in: double for the bounds that decide
@@ -165,15 +165,20 @@ MPCB_HD void prefilter_solve_consts(SolveParams &P) {
 MPCB_HD Prefilter32 prefilter32(const LaunchArgs &a, const SolveParams &P) {
     Prefilter32 f;
     f.k.smax = a.bc32[0]; f.k.smin = a.bc32[1]; f.k.dphimax = a.bc32[2];
-    f.k.cosk[0] = a.bc32[3]; f.k.sink[0] = a.bc32[4];
+    f.k.cosk[0] = a.bc32[3]; f.k.sink[0] = a.bc32[4]; f.k.cosk[1] = a.bc32[5]; f.k.sink[1] = a.bc32[6];
     f.u0 = P.pf[0]; f.w0 = P.pf[1]; f.d0 = P.pf[2]; f.e0 = P.pf[3];
     f.nx0 = P.pf[4]; f.ny0 = P.pf[5]; f.hp0 = P.pf[6];
     f.k.wl = P.pf[7]; f.k.inv_wl = P.pf[8]; f.k.wh = P.pf[9];
     return f;
 }
 
-MPCB_HD float node_prefilter32(const Prefilter32 &f, float xi, float eta, float psi, float cp, float sp) {
-    return subtree_lower_bound_t<float>(f.k, f.u0, f.w0, f.d0, f.e0, f.nx0, f.ny0, f.hp0, xi, eta, psi, cp, sp, 1);
+// steps = 1: the children of a depth-(H-1) node; steps = 2: the two levels below a depth-(H-2) node (the tile test).
+// With two steps the reach, the line bracket Q and the heading bracket G double, so the error model above reads
+//   2^-24 [kWd (8 Dmax + 12 smax) + 64 Q (E + Q) + 40 G (H + G)]
+// which is below 8 tol1 = 2^-24 [128 kWd Dmax + 64 kWd smax + 160 (E+Q)^2 + 128 (H+G)^2] term by term: the same margin
+// of 8 tol1 serves both (tests/test_pruning_bound_math.py measures either against the float64 bound).
+MPCB_HD float node_prefilter32(const Prefilter32 &f, float xi, float eta, float psi, float cp, float sp, int steps = 1) {
+    return subtree_lower_bound_t<float>(f.k, f.u0, f.w0, f.d0, f.e0, f.nx0, f.ny0, f.hp0, xi, eta, psi, cp, sp, steps);
 }
 
 }  // namespace mpcb

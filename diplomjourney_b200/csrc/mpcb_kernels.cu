@@ -221,6 +221,30 @@ __device__ __forceinline__ void node_digits(const LaunchArgs &a, unsigned long l
     }
 }
 
+// ... and the controls i_0 .. i_{H-3} of depth-(H-2) node q (fd[k + 2].d = S^(H-3-k))
+template <typename F>
+__device__ __forceinline__ void parent_digits(const LaunchArgs &a, unsigned long long q, F &&step) {
+    const int D = a.H - 2;
+    if (D <= 0) return;
+    if (a.node32) {
+        unsigned rem = (unsigned)q;
+        for (int k = 0; k + 1 < D; ++k) {
+            const unsigned i = a.fd32[k + 2].div(rem);
+            rem -= i * a.fd32[k + 2].d;
+            step(i);
+        }
+        step(rem);
+    } else {
+        unsigned long long rem = q;
+        for (int k = 0; k + 1 < D; ++k) {
+            const unsigned long long i = a.fd[k + 2].div(rem);
+            rem -= i * a.fd[k + 2].d;
+            step((unsigned)i);
+        }
+        step((unsigned)rem);
+    }
+}
+
 __device__ __forceinline__ void node_frame(const LaunchArgs &a, const SolveParams &P, unsigned long long p, NodeFrame &f) {
     double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
     node_digits(a, p, [&](unsigned i) { walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp); });
@@ -751,17 +775,28 @@ __device__ __forceinline__ void publish_best_warp(const LaunchArgs &a, long long
         const long long oj = __shfl_xor_sync(0xffffffffu, bj, o);
         lex_min(bJ, bj, oJ, oj);
     }
-    // (a result that costs more than the record already does cannot change it -- the record's cost only ever decreases --
-    //  so it does not queue for the lock: with one publish per listed node, thousands of warps took turns at the lock of
-    //  the same solve.  Equal costs go through: the lower index wins, and the pair is only read consistently under the lock.)
-    if ((threadIdx.x & 31) == 0 && bj >= 0 && !(bJ > *(volatile double *)(a.bestJ + n))) {
+    // A result that is not lexicographically below the record cannot change it -- the record only ever decreases -- so it
+    // does not queue for the lock (with one publish per listed node, or millions of exactly tied leaves, thousands of
+    // warps took turns at the lock of the same solve).  The look without the lock is safe because of the order of the
+    // accesses: the writer stores the index, fences, then stores the cost; the reader loads the cost, fences, then loads
+    // the index.  The index it sees is therefore that of the record whose cost it saw or of a LATER (smaller) record, and
+    // either way the pair (cost, index) it compares with is >= some record that really existed.
+    bool go = false;
+    if ((threadIdx.x & 31) == 0 && bj >= 0) {
+        const double rJ = *(volatile double *)(a.bestJ + n);
+        __threadfence();
+        const long long rj = *(volatile long long *)(a.bestIdx + n);
+        go = !(bJ > rJ || (bJ == rJ && rj >= 0 && bj >= rj));
+    }
+    if (go) {
         while (atomicCAS(a.lock + n, 0, 1) != 0) {}
         __threadfence();
         double cJ = *(volatile double *)(a.bestJ + n);
         long long cj = *(volatile long long *)(a.bestIdx + n);
         lex_min(cJ, cj, bJ, bj);
-        *(volatile double *)(a.bestJ + n) = cJ;
         *(volatile long long *)(a.bestIdx + n) = cj;
+        __threadfence();
+        *(volatile double *)(a.bestJ + n) = cJ;
         __threadfence();
         atomicExch(a.lock + n, 0);
     }
@@ -1184,13 +1219,19 @@ __device__ __forceinline__ bool tile_survives(const LaunchArgs &a, unsigned long
     bool keep = false;
     const unsigned long long q_hi = a.fd_S.div(p_hi - 1);
     for (unsigned long long q = a.fd_S.div(p_lo); q <= q_hi && !keep; ++q) {
-        double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
-        unsigned long long rem = q;
-        for (int k = 0; k < a.H - 2; ++k) {           // fd[k + 2].d = S^(H-3-k): digits of a depth-(H-2) node
-            unsigned long long i = a.fd[k + 2].div(rem);
-            rem -= i * a.fd[k + 2].d;
-            walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp);
+        // the fp32 pre-filter first (mpcb_bounds.cuh, two steps): all but a few per cent of the tiles are nowhere near the
+        // bound, and a tile it drops the float64 test below drops too
+        if (a.prefilter) {
+            const Prefilter32 pf = prefilter32(a, P);
+            float xi = 0.f, eta = 0.f, psi = 0.f, cp = 1.f, sp = 0.f;
+            parent_digits(a, q, [&](unsigned i) {
+                const float4 t = __ldg(a.g.tab32 + i);
+                walk_step_t<float>(t.x, t.y, t.z, t.w, xi, eta, psi, cp, sp);
+            });
+            if (node_prefilter32(pf, xi, eta, psi, cp, sp, 2) > __double2float_ru(bound + 8.0 * P.tol1)) continue;
         }
+        double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
+        parent_digits(a, q, [&](unsigned i) { walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp); });
         keep = !(subtree_lower_bound(a, P, xi, eta, psi, cp, sp, 2) > bound);      // NaN bounds never cut
     }
     if (!keep) cut_nodes = (unsigned)(p_hi - p_lo);

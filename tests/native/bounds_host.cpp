@@ -20,7 +20,7 @@ extern "C" void mpcb_test_subtree_lower_bounds(double smax, double smin, double 
 // the fp32 pre-filter of the pruned pass 1 on the same nodes (poses given in float64, rounded to float as the float walk
 // would hold them)
 extern "C" void mpcb_test_prefilter32(double smax, double smin, double dphimax, const double *solve, long long n,
-                                      const double *xi, const double *eta, const double *psi, float *out) {
+                                      const double *xi, const double *eta, const double *psi, float *out, int steps) {
     mpcb::LaunchArgs a = {};
     a.g.smax = smax; a.g.smin = smin; a.g.dphimax = dphimax;
     mpcb::bounds_set_heading_ranges(a, dphimax);
@@ -31,5 +31,5 @@ extern "C" void mpcb_test_prefilter32(double smax, double smin, double dphimax, 
     const mpcb::Prefilter32 f = mpcb::prefilter32(a, P);
     for (long long i = 0; i < n; ++i)
         out[i] = mpcb::node_prefilter32(f, (float)xi[i], (float)eta[i], (float)psi[i], std::cos((float)psi[i]),
-                                        std::sin((float)psi[i]));
+                                        std::sin((float)psi[i]), steps);
 }

@@ -173,10 +173,10 @@ def shipped_bound():
         out = np.empty_like(xi)
         p = lambda a: a.ctypes.data_as(dp)
         lib.mpcb_test_subtree_lower_bounds(smax, smin, dmax, p(solve), len(xi), p(xi), p(eta), p(psi), k, p(out))
-        if k == 1:          # ... and the fp32 pre-filter of the pruned pass 1 on the same nodes, with the model's error bound
+        if k in (1, 2):     # ... and the fp32 pre-filter (nodes: one step, tiles: two) on the same nodes, with the model's error bound
             out32 = np.empty(len(xi), np.float32)
             lib.mpcb_test_prefilter32(smax, smin, dmax, p(solve), len(xi), p(xi), p(eta), p(psi),
-                                      out32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+                                      out32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), k)
             H = 3
             Rtot = H * smax
             E1 = abs(e0) + wl * Rtot + wl * smax
@@ -185,7 +185,8 @@ def shipped_bound():
             tol1 = 2.0 ** -22 * (4e4 * Dmax + 2e4 * smax + 5 * E1 * E1 + 4 * H1 * H1)      # prep_kernel's tol1 (prefix)
             bound.prefilter = (out32.astype(np.float64), out, tol1)
         return kbase + out
-    lib.mpcb_test_prefilter32.argtypes = [ctypes.c_double] * 3 + [dp, ctypes.c_longlong, dp, dp, dp, ctypes.POINTER(ctypes.c_float)]
+    lib.mpcb_test_prefilter32.argtypes = [ctypes.c_double] * 3 + [dp, ctypes.c_longlong, dp, dp, dp, ctypes.POINTER(ctypes.c_float),
+                                          ctypes.c_int]
     return bound
 
 
@@ -218,14 +219,15 @@ def test_fp32_prefilter_stays_within_its_margin_of_the_float64_bound(shipped_bou
     sc = C.random_scenarios(10, 29)
     sc[0, 3:5] = sc[0, :2] + [0.05, 0.02]
     sc[1, 3:5] = sc[1, :2] + [60.0, -45.0]                            # a far target: large kWd d
-    worst = 0.0
-    for x in sc:
-        new, true_min, poses, consts = _bounds(V, B, 3, x, 1, cost, want_poses=True)
-        shipped_bound(x, cost, poses, consts, 1)
-        lb32, lb64, tol1 = shipped_bound.prefilter
-        ok = np.isfinite(lb64)
-        err = np.abs(lb32[ok] - lb64[ok]).max()
-        worst = max(worst, err / tol1)
-        assert err <= tol1, (grid, cost, err, tol1)                   # the analysis in mpcb_bounds.cuh; the kernel allows 8x
-    assert worst > 0.0
-    print(f"fp32 pre-filter: worst |lb32 - lb64| = {worst:.3f} tol1 ({grid}, {cost})")
+    for steps in (1, 2):                                              # node test (children) and tile test (two levels)
+        worst = 0.0
+        for x in sc:
+            new, true_min, poses, consts = _bounds(V, B, 3, x, steps, cost, want_poses=True)
+            shipped_bound(x, cost, poses, consts, steps)
+            lb32, lb64, tol1 = shipped_bound.prefilter
+            ok = np.isfinite(lb64)
+            err = np.abs(lb32[ok] - lb64[ok]).max()
+            worst = max(worst, err / tol1)
+            assert err <= tol1, (grid, cost, steps, err, tol1)        # the analysis in mpcb_bounds.cuh; the kernel allows 8x
+        assert worst > 0.0
+        print(f"fp32 pre-filter, {steps} step(s): worst |lb32 - lb64| = {worst:.3f} tol1 ({grid}, {cost})")
