@@ -196,55 +196,6 @@ struct NodeFrame {
     bool unmoved;              // the node has not moved at all (the reference's "on the line origin" special case)
 };
 
-// the controls i_0 .. i_{H-2} of depth-(H-1) node p, first step first: step(i) once per digit.  fd[k + 1].d = S^(H-2-k), so
-// the last digit is what is left (no division by 1), and indices below 2^32 take the 5-instruction 32-bit dividers
-template <typename F>
-__device__ __forceinline__ void node_digits(const LaunchArgs &a, unsigned long long p, F &&step) {
-    const int D = a.H - 1;
-    if (D <= 0) return;
-    if (a.node32) {
-        unsigned rem = (unsigned)p;
-        for (int k = 0; k + 1 < D; ++k) {
-            const unsigned i = a.fd32[k + 1].div(rem);
-            rem -= i * a.fd32[k + 1].d;
-            step(i);
-        }
-        step(rem);
-    } else {
-        unsigned long long rem = p;
-        for (int k = 0; k + 1 < D; ++k) {
-            const unsigned long long i = a.fd[k + 1].div(rem);
-            rem -= i * a.fd[k + 1].d;
-            step((unsigned)i);
-        }
-        step((unsigned)rem);
-    }
-}
-
-// ... and the controls i_0 .. i_{H-3} of depth-(H-2) node q (fd[k + 2].d = S^(H-3-k))
-template <typename F>
-__device__ __forceinline__ void parent_digits(const LaunchArgs &a, unsigned long long q, F &&step) {
-    const int D = a.H - 2;
-    if (D <= 0) return;
-    if (a.node32) {
-        unsigned rem = (unsigned)q;
-        for (int k = 0; k + 1 < D; ++k) {
-            const unsigned i = a.fd32[k + 2].div(rem);
-            rem -= i * a.fd32[k + 2].d;
-            step(i);
-        }
-        step(rem);
-    } else {
-        unsigned long long rem = q;
-        for (int k = 0; k + 1 < D; ++k) {
-            const unsigned long long i = a.fd[k + 2].div(rem);
-            rem -= i * a.fd[k + 2].d;
-            step((unsigned)i);
-        }
-        step((unsigned)rem);
-    }
-}
-
 __device__ __forceinline__ void node_frame(const LaunchArgs &a, const SolveParams &P, unsigned long long p, NodeFrame &f) {
     double xi = 0.0, eta = 0.0, psi = 0.0, cp = 1.0, sp = 0.0;
     node_digits(a, p, [&](unsigned i) { walk_step(ldg_d4(a.g.tab64 + i), xi, eta, psi, cp, sp); });
@@ -800,24 +751,6 @@ __device__ __forceinline__ void publish_best_warp(const LaunchArgs &a, long long
         __threadfence();
         atomicExch(a.lock + n, 0);
     }
-}
-
-// float64 pose of depth-(H-1) node p by the reference's own steps: exactly what exact_cost computes on the way to any
-// leaf below it, so  exact_child_cost(pose, c) == exact_cost(p * S + c)  bit for bit (FULL trees)
-// (both out of line, like exact_cost: inlined, their double-precision sincos took the scan loop's registers)
-__device__ __noinline__ void exact_node_pose(const LaunchArgs &a, const SolveParams &P, unsigned long long p, double &x,
-                                             double &y, double &phi) {
-    const bool slow = (P.flags & kFlagSlow) != 0;
-    const double4 *tab = slow ? a.g.tab64_slow : a.g.tab64;
-    const double *vt = slow ? a.g.vtab_slow : a.g.vtab;
-    x = P.xs; y = P.ys; phi = P.phi0;
-    node_digits(a, p, [&](unsigned i) { exact_step(a, tab, vt, i, x, y, phi); });
-}
-__device__ __noinline__ double exact_child_cost(const LaunchArgs &a, const SolveParams &P, double x, double y, double phi,
-                                                unsigned c) {
-    const bool slow = (P.flags & kFlagSlow) != 0;
-    exact_step(a, slow ? a.g.tab64_slow : a.g.tab64, slow ? a.g.vtab_slow : a.g.vtab, c, x, y, phi);
-    return exact_terminal(a, P, x, y, phi);
 }
 
 // the S leaves of one node spread over the lanes of a warp: in-window leaves become candidates.  Those that do not fit

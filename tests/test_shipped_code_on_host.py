@@ -37,6 +37,9 @@ def host():
                                          ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_double]
     lib.mpcb_test_exact_cost.restype = ctypes.c_double
     lib.mpcb_test_apply_event.argtypes = [ctypes.c_int] + [ctypes.c_double] * 6 + [ctypes.c_int, dp]
+    lib.mpcb_test_exact_from_node.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                              ctypes.c_int, dp, dp, dp, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                              ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), dp, dp, u32p, u32p]
     return lib
 
 
@@ -146,3 +149,36 @@ def test_operator_events_reproduce_the_reference(host, golden):
                                           line.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
         np.testing.assert_allclose(line, c["out"], rtol=0, atol=2e-15, err_msg=str(c))
         assert slow == c["steps_for_slowing"], c
+
+
+@pytest.mark.parametrize("node32", [1, 0])
+@pytest.mark.parametrize("H", [2, 3, 5])
+def test_leaf_from_its_nodes_pose_equals_the_whole_walk(host, node32, H):
+    """The refinement scan evaluates an in-window leaf from the float64 pose of its depth-(H-1) node (computed once per
+    node) with ONE more step; that must be the very number exact_cost gets from walking all H steps -- bit for bit --
+    and the node's controls (and those of its parent, which the tile test walks) must be the base-S digits of its index,
+    with the 32-bit and the 64-bit dividers alike."""
+    rng = np.random.default_rng(40 + H)
+    V, B = np.linspace(0.0, 1.0, 7), np.linspace(-1.0, 1.0, 9)
+    S = V.size * B.size
+    dp = ctypes.POINTER(ctypes.c_double)
+    p = lambda a: a.ctypes.data_as(dp)
+    for cost in (0, 1):
+        for slow in (0, 1):
+            st, tg, og = rng.uniform(-3, 3, 3), rng.uniform(-3, 3, 2), rng.uniform(-1, 1, 2)
+            j = rng.integers(0, S ** H, 400).astype(np.int64)
+            j[:3] = (0, S ** H - 1, S ** (H - 1))
+            out, whole = np.empty(j.size), np.empty(j.size)
+            digits = np.zeros(j.size * (H - 1), np.uint32)
+            pdigits = np.zeros(max(1, j.size * (H - 2)), np.uint32)
+            v, b = np.ascontiguousarray(V), np.ascontiguousarray(B)
+            host.mpcb_test_exact_from_node(p(v), v.size, p(b), b.size, L, DT, cost, H, p(st), p(tg), p(og), slow,
+                                           C.CONFIG["v_min"], node32, j.size,
+                                           j.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), p(out), p(whole),
+                                           digits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                           pdigits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+            assert np.array_equal(out.view(np.uint64), whole.view(np.uint64))
+            want = np.array([[(int(q) // S) // S ** (H - 2 - k) % S for k in range(H - 1)] for q in j], np.uint32)
+            np.testing.assert_array_equal(digits.reshape(j.size, H - 1), want)
+            if H > 2:       # the tile test walks the node's parent: the same digits without the last
+                np.testing.assert_array_equal(pdigits.reshape(j.size, H - 2), want[:, :-1])
