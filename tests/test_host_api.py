@@ -209,6 +209,30 @@ def test_tree_module_actual_batch_on_oracle_backend(golden):
     _actual_batch_equals_fixture_and_sequential(mt, golden)
 
 
+def test_tree_module_programmed_batch_with_events_on_oracle_backend(golden):
+    """math_mpc_batch(..., events=True, host_loop=True): the noise-free programmed run as a batch on the per-tick path
+    (one batched solve with per-robot windows per tick, operator events applied per robot by the module's own functions)
+    == the reference's 150-tick log; a second robot that starts elsewhere does not disturb it.  (The device-resident
+    flavour of the same call is checked against this path on the GPU.)"""
+    mt = importlib.reload(importlib.import_module("diplomjourney_b200.math_model_tree"))
+    mt._backend = OracleBackend()
+    log = golden("held_closed_loop")["log"]
+    r = mt.math_mpc_batch([[0, 0, 0, 0, 0], [0.4, -0.3, 0.8, 0, 0]], [[2, 3], [1.5, 2.0]], max_ticks=200, events=True,
+                          host_loop=True)
+    ref = np.array([log[k][1:] for k in ("result_trajectory_x", "result_trajectory_y", "result_trajectory_phi",
+                                         "result_trajectory_v", "result_trajectory_beta")], dtype=float).T
+    fin = log["final"]
+    assert r["ticks"][0] == ref.shape[0] == fin["p"] - 1
+    np.testing.assert_allclose(r["log"][0, :ref.shape[0]], ref, rtol=0, atol=1e-9)
+    rob = r["robots"][0]
+    assert (rob["m"], rob["steps_for_slowing"], rob["recursive"]) == (fin["m"], fin["steps_for_slowing"], fin["recursive"])
+    assert (rob["x_0"], rob["y_0"]) == pytest.approx((fin["x_0"], fin["y_0"]), abs=1e-9)
+    assert r["ticks"][1] > 0 and np.isfinite(r["log"][1, :r["ticks"][1]]).all()
+    # the script the device loop is handed for events=True is the one the module's own event function executes
+    assert [e[0] for e in mt.DEMO_EVENTS] == [60, 90, 110]
+    assert [e[1] for e in mt.DEMO_EVENTS] == [mt._native.EVENT_TURN_RIGHT, mt._native.EVENT_TURN_LEFT, mt._native.EVENT_NEW_TARGET]
+
+
 def test_tree_module_empty_window_returns_the_previous_trajectory():
     """An empty velocity window has no candidates: the reference's loops do not execute (its np.min sits inside the
     velocity loop, math_model_tree.py:312-313), nothing improves and the previous trajectory is handed back."""
