@@ -503,6 +503,9 @@ def math_mpc_batch(initial_coordinates, target_coordinates, max_ticks=512, origi
     finally:
         g.update(x_t=saved[0], y_t=saved[1], x_0=saved[2], y_0=saved[3])
     if isActual or host_loop:
+        if not isinstance(events, bool) and events is not None:
+            raise ValueError("a custom event script runs on the device loop only (isActual=False, host_loop=False); "
+                             "the per-tick path applies the demo script (events=True) with the module's own functions")
         return _math_mpc_batch_ticks(ini, tgt, org, first, max_ticks, cost_kind, isActual, rngs, bool(events))
     params = _native.LoopParams.from_config(_cfg, _native.COST_TREE if cost_kind is None else cost_kind,
                                             prediction_horizon, max_ticks)

@@ -228,6 +228,8 @@ def test_tree_module_programmed_batch_with_events_on_oracle_backend(golden):
     assert (rob["m"], rob["steps_for_slowing"], rob["recursive"]) == (fin["m"], fin["steps_for_slowing"], fin["recursive"])
     assert (rob["x_0"], rob["y_0"]) == pytest.approx((fin["x_0"], fin["y_0"]), abs=1e-9)
     assert r["ticks"][1] > 0 and np.isfinite(r["log"][1, :r["ticks"][1]]).all()
+    with pytest.raises(ValueError):          # a custom script is a device-loop feature
+        mt.math_mpc_batch([[0, 0, 0, 0, 0]], [[2, 3]], events=[(5, mt._native.EVENT_NEW_TARGET, 1.0, 1.0)], host_loop=True)
     # the script the device loop is handed for events=True is the one the module's own event function executes
     assert [e[0] for e in mt.DEMO_EVENTS] == [60, 90, 110]
     assert [e[1] for e in mt.DEMO_EVENTS] == [mt._native.EVENT_TURN_RIGHT, mt._native.EVENT_TURN_LEFT, mt._native.EVENT_NEW_TARGET]
